@@ -1,0 +1,30 @@
+// extern "C" surface of libcosma_b200.so (declared in include/cosma_b200.h).
+#include "../../include/cosma_b200.h"
+#include "gemm_f64_sm100.h"
+
+#include <string>
+
+namespace {
+thread_local std::string g_last_error;
+thread_local int g_last_gemm_path = 0;
+}  // namespace
+
+namespace cosma_b200 {
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace cosma_b200
+
+extern "C" {
+
+const char* cosma_b200_version(void) { return "cosma_b200 0.1.0 sm_100a"; }
+const char* cosma_b200_last_error(void) { return g_last_error.c_str(); }
+int cosma_b200_last_gemm_path(void) { return g_last_gemm_path; }
+
+int cosma_b200_dgemm(void* stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const double* alpha,
+                     const double* A, int64_t lda, const double* B, int64_t ldb, const double* beta, double* C,
+                     int64_t ldc) {
+    if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
+    return cosma_b200::dgemm_sm100(static_cast<cudaStream_t>(stream), transa, transb, m, n, k, *alpha, A, lda, B, ldb,
+                                   *beta, C, ldc, &g_last_gemm_path);
+}
+
+}  // extern "C"

@@ -1,0 +1,437 @@
+// K1/K2: FP64 DGEMM / ZGEMM for sm_100a, device-resident operands, column-major.
+//
+//   C = alpha * op(A) * op(B) + beta * C        (op = N | T | C)
+//
+// Replaces the reference's base-case GEMM: local_multiply -> gpu::gemm (Tiled-MM host-streamed
+// cublas?gemm), reference src/cosma/local_multiply.cpp:219-269, libs/Tiled-MM/src/Tiled-MM/
+// tiled_mm.cpp:181-268,492-624. The reference streams <=5000^3 host tiles over PCIe; here A/B/C
+// stay resident in HBM and one persistent kernel does the whole contraction.
+//
+// Design (see DESIGN.md "K1"):
+//  * FP64 on Blackwell is not a tcgen05 kind; the native FP64 tensor instruction is DMMA.8x8x4
+//    (mma.sync.m8n8k4.f64), 64 FMA/clk/SM. Accumulators therefore live in registers.
+//  * Persistent CTAs (one per SM), 128x128 C tile, BK=16 per pipeline stage, 6 stages (192 KB smem).
+//  * Warp-specialised: warp 8 = TMA producer (cp.async.bulk.tensor + mbarrier expect_tx),
+//    warps 0-7 = DMMA consumers, each owning a 64(m) x 32(n) register tile (32 DMMA accumulators).
+//  * Operand tiles are written by TMA with the 128-byte swizzle, laid out so that every DMMA
+//    fragment load (ld.shared.f64, one element per thread) is bank-conflict free; the k index
+//    inside each 16-wide k block is permuted per thread (k is a summation index, any bijection
+//    that A and B share is legal) to make that possible for both operand layouts at once.
+//  * The MMA computes C^T tiles (MMA-M <- n, MMA-N <- m) so that each thread's two accumulator
+//    values are adjacent in column-major C and the epilogue uses 16-byte accesses.
+//  * alpha/beta in the epilogue; beta == 0 never reads C (ScaLAPACK NaN rule, reference
+//    utils/pxgemm_utils.hpp:603-637). transpose/conjugate are folded into the TMA tensor maps and
+//    the fragment addressing -- no extra pass, no extra flops.
+//  * ZGEMM runs on the same pipeline through the real 2m x 2k x n embedding
+//    [Cr;Ci] = [[Ar,-Ai],[Ai,Ar]] * [Br;Bi] evaluated on the fly from interleaved complex tiles:
+//    exactly 4 real FMA per complex FMA, i.e. no wasted DMMA work.
+#include "sm100_common.cuh"
+#include "gemm_f64_sm100.h"
+
+#include <cstdio>
+#include <mutex>
+
+namespace cosma_b200 {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 16;
+constexpr int STAGES = 6;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup
+constexpr int WARPS_M = 2;  // warp grid over the CTA tile
+constexpr int WARPS_N = 4;
+constexpr int WM = BM / WARPS_M;  // 64
+constexpr int WN = BN / WARPS_N;  // 32
+constexpr int MI = WM / 8;        // 8 fragments along m
+constexpr int NI = WN / 8;        // 4 fragments along n
+constexpr int OPERAND_STAGE_BYTES = 128 * BK * 8;  // 16 KB per operand per stage
+constexpr int STAGE_BYTES = 2 * OPERAND_STAGE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// Operand tile layouts in shared memory (both written by TMA with CU_TENSOR_MAP_SWIZZLE_128B):
+//  MN-major ("the m (or n) index is contiguous in global memory"):
+//      8 boxes, box b = [16 k-rows][16 x] doubles = 2 KB;      x = 16*b + xx
+//      byte(x,k) = b*2048 + k*128 + (((xx>>1) ^ (k&7)) << 4) + (xx&1)*8
+//  K-major ("k is contiguous in global memory"):
+//      1 box [128 x-rows][16 k] doubles = 16 KB
+//      byte(x,k) = x*128 + (((k>>1) ^ (x&7)) << 4) + (k&1)*8
+enum Layout { MN_MAJOR = 0, K_MAJOR = 1 };
+
+// k permutation: MMA step j (0..3) of a 16-wide k block, thread column t = lane%4 handles
+//   k = (t0^j0) | t0<<1 | t1<<2 | (t1^j1)<<3.
+// For fixed j the four t's give distinct bits (2,1) [MN-major conflict freedom] and distinct
+// bits (3,0) [K-major conflict freedom]; over j = 0..3 every k in 0..15 is used exactly once.
+__device__ __forceinline__ int kperm(int t, int j) {
+    const int t0 = t & 1, t1 = t >> 1, j0 = j & 1, j1 = j >> 1;
+    return (t0 ^ j0) | (t0 << 1) | (t1 << 2) | ((t1 ^ j1) << 3);
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t frag_offset(int idx, int g, int kk) {
+    if (LAYOUT == MN_MAJOR) {
+        const int xx = ((idx & 1) << 3) | g;
+        return (idx >> 1) * 2048 + kk * 128 + ((((xx >> 1) ^ (kk & 7))) << 4) + ((xx & 1) << 3);
+    } else {
+        const int x = idx * 8 + g;
+        return x * 128 + ((((kk >> 1) ^ g)) << 4) + ((kk & 1) << 3);
+    }
+}
+
+struct GemmParams {
+    int64_t m, n, k;
+    double alpha, beta;
+    double* C;
+    int64_t ldc;
+    int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+    // bands of 16 tile-rows, column-major inside a band: the ~148 tiles in flight at any time
+    // cover a ~16 x 9 block, so A row-panels and B column-panels are shared through L2.
+    constexpr int G = 16;
+    const int band_tiles = G * tiles_n;
+    const int band = tile / band_tiles;
+    const int rem = tile - band * band_tiles;
+    const int rows_in_band = min(G, tiles_m - band * G);
+    tn = rem / rows_in_band;
+    tm = band * G + rem % rows_in_band;
+}
+
+template <int LAYOUT_A, int LAYOUT_B>
+__global__ void __launch_bounds__(THREADS, 1)
+dgemm_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B needs 1024-byte aligned boxes
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_kb = static_cast<int>((p.k + BK - 1) / BK);
+
+    if (warp >= CONSUMER_WARPS) {
+        // ===== producer warpgroup: give registers back, warp 8 lane 0 drives TMA =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == CONSUMER_WARPS && lane == 0) {
+            tma_prefetch_desc(&map_a);
+            tma_prefetch_desc(&map_b);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int tm, tn;
+                tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+                const int m0 = tm * BM, n0 = tn * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + OPERAND_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    const int k0 = kb * BK;
+                    if (LAYOUT_A == MN_MAJOR) {
+#pragma unroll
+                        for (int b = 0; b < BM / 16; ++b) tma_load_2d(sa + b * 2048, &map_a, &full_bar[s], m0 + 16 * b, k0);
+                    } else {
+                        tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
+                    }
+                    if (LAYOUT_B == MN_MAJOR) {
+#pragma unroll
+                        for (int b = 0; b < BN / 16; ++b) tma_load_2d(sb + b * 2048, &map_b, &full_bar[s], n0 + 16 * b, k0);
+                    } else {
+                        tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== DMMA consumers =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int wm = warp % WARPS_M;
+    const int wn = warp / WARPS_M;
+
+    // per-thread fragment byte offsets inside an operand stage buffer, for each k step j
+    // (idx-dependent parts are compile-time after unrolling)
+    const uint32_t smem_base = smem_u32(smem);
+
+    double acc[NI][MI][2];
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int tm, tn;
+        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) acc[ni][mi][0] = acc[ni][mi][1] = 0.0;
+
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            const uint32_t sa = smem_base + s * STAGE_BYTES;
+            const uint32_t sb = sa + OPERAND_STAGE_BYTES;
+
+            double fa[2][MI], fb[2][NI];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) fa[0][mi] = lds_f64(sa + frag_offset<LAYOUT_A>(wm * MI + mi, g, kperm(t, 0)));
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) fb[0][ni] = lds_f64(sb + frag_offset<LAYOUT_B>(wn * NI + ni, g, kperm(t, 0)));
+#pragma unroll
+            for (int j = 0; j < BK / 4; ++j) {
+                const int cur = j & 1, nxt = cur ^ 1;
+                if (j + 1 < BK / 4) {
+                    const int kk = kperm(t, j + 1);
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi) fa[nxt][mi] = lds_f64(sa + frag_offset<LAYOUT_A>(wm * MI + mi, g, kk));
+#pragma unroll
+                    for (int ni = 0; ni < NI; ++ni) fb[nxt][ni] = lds_f64(sb + frag_offset<LAYOUT_B>(wn * NI + ni, g, kk));
+                }
+#pragma unroll
+                for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi) dmma884(acc[ni][mi][0], acc[ni][mi][1], fb[cur][ni], fa[cur][mi]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+
+        // ===== epilogue: C = alpha*acc + beta*C, 16-byte accesses along m =====
+        const int64_t mbase = int64_t(tm) * BM + wm * WM + 2 * t;
+        const int64_t nbase = int64_t(tn) * BN + wn * WN + g;
+        const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+            const int64_t nn = nbase + ni * 8;
+            if (nn >= p.n) continue;
+            double* ccol = p.C + nn * p.ldc;
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) {
+                const int64_t mm = mbase + mi * 8;
+                double v0 = p.alpha * acc[ni][mi][0];
+                double v1 = p.alpha * acc[ni][mi][1];
+                if (mm + 1 < p.m && vec_ok) {
+                    double2* ptr = reinterpret_cast<double2*>(ccol + mm);
+                    if (p.beta != 0.0) {
+                        const double2 old = *ptr;
+                        v0 += p.beta * old.x;
+                        v1 += p.beta * old.y;
+                    }
+                    *ptr = make_double2(v0, v1);
+                } else {
+                    if (mm < p.m) {
+                        if (p.beta != 0.0) v0 += p.beta * ccol[mm];
+                        ccol[mm] = v0;
+                    }
+                    if (mm + 1 < p.m) {
+                        if (p.beta != 0.0) v1 += p.beta * ccol[mm + 1];
+                        ccol[mm + 1] = v1;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic path: any leading dimension / alignment (TMA needs 16-byte aligned bases and strides).
+// Plain shared-memory tiled DFMA kernel; only odd-lda or unaligned operands come here.
+// ---------------------------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16;
+__global__ void __launch_bounds__(256) dgemm_generic_kernel(int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha,
+                                                             const double* __restrict__ A, int64_t lda,
+                                                             const double* __restrict__ B, int64_t ldb, double beta,
+                                                             double* __restrict__ C, int64_t ldc) {
+    __shared__ double sA[GK][GT + 1];
+    __shared__ double sB[GK][GT + 1];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int64_t m0 = int64_t(blockIdx.x) * GT, n0 = int64_t(blockIdx.y) * GT;
+    double acc[4][4] = {};
+    for (int64_t k0 = 0; k0 < k; k0 += GK) {
+        for (int e = threadIdx.x; e < GT * GK; e += 256) {
+            int x, kk;
+            if (ta) { kk = e % GK; x = e / GK; } else { x = e % GT; kk = e / GT; }
+            const int64_t gm = m0 + x, gk = k0 + kk;
+            double v = 0.0;
+            if (gm < m && gk < k) v = ta ? A[gk + gm * lda] : A[gm + gk * lda];
+            sA[kk][x] = v;
+        }
+        for (int e = threadIdx.x; e < GT * GK; e += 256) {
+            int x, kk;
+            if (tb) { x = e % GT; kk = e / GT; } else { kk = e % GK; x = e / GK; }
+            const int64_t gn = n0 + x, gk = k0 + kk;
+            double v = 0.0;
+            if (gn < n && gk < k) v = tb ? B[gn + gk * ldb] : B[gk + gn * ldb];
+            sB[kk][x] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[kk][tx + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[kk][ty + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t gn = n0 + ty + 16 * j;
+        if (gn >= n) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t gm = m0 + tx + 16 * i;
+            if (gm >= m) continue;
+            double v = alpha * acc[i][j];
+            if (beta != 0.0) v += beta * C[gm + gn * ldc];
+            C[gm + gn * ldc] = v;
+        }
+    }
+}
+
+__global__ void scale_matrix_kernel(int64_t m, int64_t n, double beta, double* C, int64_t ldc) {
+    const int64_t total = m * n;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        double* ptr = C + (i % m) + (i / m) * ldc;
+        *ptr = (beta == 0.0) ? 0.0 : beta * *ptr;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+// 2-D FP64 tensor map: dim0 (contiguous) extent d0, dim1 extent d1 with stride ld elements.
+bool make_map(CUtensorMap* map, const double* base, int64_t d0, int64_t d1, int64_t ld, int box0, int box1) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 8};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int LA, int LB>
+cudaError_t launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int sms, cudaStream_t stream) {
+    auto kern = dgemm_sm100_kernel<LA, LB>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    const int grid = tiles < sms ? tiles : sms;
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(ma, mb, p);
+    return cudaGetLastError();
+}
+
+int device_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+}  // namespace
+
+int dgemm_sm100(cudaStream_t stream, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
+                const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                int* path_used) {
+    const bool ta = !(transa == 'N' || transa == 'n');
+    const bool tb = !(transb == 'N' || transb == 'n');
+    if (m < 0 || n < 0 || k < 0) return COSMA_B200_INVALID_ARG;
+    if (lda < (ta ? (k > 1 ? k : 1) : (m > 1 ? m : 1)) || ldb < (tb ? (n > 1 ? n : 1) : (k > 1 ? k : 1)) ||
+        ldc < (m > 1 ? m : 1))
+        return COSMA_B200_INVALID_ARG;
+    if (m == 0 || n == 0) return COSMA_B200_OK;
+    if (path_used) *path_used = 0;
+    if (k == 0 || alpha == 0.0) {
+        // BLAS semantics: C = beta*C (C not read when beta == 0)
+        if (beta != 1.0) {
+            scale_matrix_kernel<<<device_sm_count() * 4, 256, 0, stream>>>(m, n, beta, C, ldc);
+            if (cudaGetLastError() != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+        }
+        return COSMA_B200_OK;
+    }
+    const bool aligned = ((lda & 1) == 0) && ((ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    if (aligned) {
+        CUtensorMap ma, mb;
+        bool ok;
+        // A: 'N' -> stored m x k (m contiguous) MN-major; 'T' -> stored k x m (k contiguous) K-major
+        ok = ta ? make_map(&ma, A, k, m, lda, 16, BM) : make_map(&ma, A, m, k, lda, 16, BK);
+        // B: 'N' -> stored k x n (k contiguous) K-major; 'T' -> stored n x k (n contiguous) MN-major
+        ok = ok && (tb ? make_map(&mb, B, n, k, ldb, 16, BK) : make_map(&mb, B, k, n, ldb, 16, BN));
+        if (ok) {
+            GemmParams p;
+            p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc;
+            p.tiles_m = static_cast<int>((m + BM - 1) / BM);
+            p.tiles_n = static_cast<int>((n + BN - 1) / BN);
+            const int sms = device_sm_count();
+            cudaError_t e;
+            if (!ta && !tb) e = launch_tma<MN_MAJOR, K_MAJOR>(ma, mb, p, sms, stream);
+            else if (!ta && tb) e = launch_tma<MN_MAJOR, MN_MAJOR>(ma, mb, p, sms, stream);
+            else if (ta && !tb) e = launch_tma<K_MAJOR, K_MAJOR>(ma, mb, p, sms, stream);
+            else e = launch_tma<K_MAJOR, MN_MAJOR>(ma, mb, p, sms, stream);
+            if (e != cudaSuccess) {
+                fprintf(stderr, "cosma_b200: dgemm_sm100 launch failed: %s\n", cudaGetErrorString(e));
+                return COSMA_B200_CUDA_ERROR;
+            }
+            if (path_used) *path_used = 1;
+            return COSMA_B200_OK;
+        }
+    }
+    dim3 grid(static_cast<unsigned>((m + GT - 1) / GT), static_cast<unsigned>((n + GT - 1) / GT));
+    dgemm_generic_kernel<<<grid, 256, 0, stream>>>(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (cudaGetLastError() != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+    if (path_used) *path_used = 2;
+    return COSMA_B200_OK;
+}
+
+}  // namespace cosma_b200

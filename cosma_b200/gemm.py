@@ -1,0 +1,42 @@
+"""Local GEMM through the C ABI (cosma_b200_dgemm / cosma_b200_zgemm), column-major, device pointers.
+
+Mirrors the call the reference makes at the base case: local_multiply(ctx, A, B, C, m, n, k, alpha, beta)
+(reference src/cosma/local_multiply.hpp:7-16) -> gemm('N','N', m, n, k, alpha, A, lda=m, B, ldb=k, beta, C, ldc=m)."""
+import ctypes
+
+from . import _lib
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if isinstance(stream, int):
+        return ctypes.c_void_p(stream)
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
+def gemm_raw(dtype, transa, transb, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc, stream=None):
+    """dtype: 'd' or 'z'. a_ptr/b_ptr/c_ptr: device addresses (int). alpha/beta: python float or complex."""
+    lib = _lib.load()
+    if dtype == "d":
+        al = (ctypes.c_double * 1)(float(alpha))
+        be = (ctypes.c_double * 1)(float(beta))
+        fn = lib.cosma_b200_dgemm
+    elif dtype == "z":
+        al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+        be = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
+        fn = lib.cosma_b200_zgemm
+    else:
+        raise ValueError(dtype)
+    st = fn(_stream_ptr(stream), transa.encode(), transb.encode(), m, n, k, al, ctypes.c_void_p(a_ptr), lda,
+            ctypes.c_void_p(b_ptr), ldb, be, ctypes.c_void_p(c_ptr), ldc)
+    _lib.check(st, "cosma_b200_%sgemm" % dtype)
+
+
+def local_multiply(A, B, C, m, n, k, alpha, beta, stream=None):
+    """A, B, C: 1-D torch CUDA tensors holding column-major m x k, k x n, m x n (lda=m, ldb=k, ldc=m)."""
+    import torch
+    dt = {torch.float64: "d", torch.complex128: "z"}[C.dtype]
+    gemm_raw(dt, "N", "N", m, n, k, alpha, A.data_ptr(), max(m, 1), B.data_ptr(), max(k, 1), beta, C.data_ptr(),
+             max(m, 1), stream)
