@@ -27,4 +27,12 @@ int cosma_b200_dgemm(void* stream, char transa, char transb, int64_t m, int64_t 
                                    *beta, C, ldc, &g_last_gemm_path);
 }
 
+int cosma_b200_zgemm(void* stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const double* alpha,
+                     const double* A, int64_t lda, const double* B, int64_t ldb, const double* beta, double* C,
+                     int64_t ldc) {
+    if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
+    return cosma_b200::zgemm_sm100(static_cast<cudaStream_t>(stream), transa, transb, m, n, k, alpha, A, lda, B, ldb, beta,
+                                   C, ldc, &g_last_gemm_path);
+}
+
 }  // extern "C"

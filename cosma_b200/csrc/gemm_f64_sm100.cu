@@ -50,14 +50,20 @@ constexpr int OPERAND_STAGE_BYTES = 128 * BK * 8;  // 16 KB per operand per stag
 constexpr int STAGE_BYTES = 2 * OPERAND_STAGE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
-// Operand tile layouts in shared memory (both written by TMA with CU_TENSOR_MAP_SWIZZLE_128B):
-//  MN-major ("the m (or n) index is contiguous in global memory"):
-//      8 boxes, box b = [16 k-rows][16 x] doubles = 2 KB;      x = 16*b + xx
-//      byte(x,k) = b*2048 + k*128 + (((xx>>1) ^ (k&7)) << 4) + (xx&1)*8
-//  K-major ("k is contiguous in global memory"):
-//      1 box [128 x-rows][16 k] doubles = 16 KB
+// Operand tile layouts in shared memory (written by TMA with CU_TENSOR_MAP_SWIZZLE_128B; "x" is the m or n
+// index of the tile, "k" the contraction index, both in REAL (double) units):
+//  MN-major ("x is contiguous in global memory"), boxes of 16 x-values by R k-rows (R = 16 real, 8 complex):
+//      byte(x,k) = (x/16)*R*128 + k*128 + ((((x%16)>>1) ^ (k&7)) << 4) + (x&1)*8
+//  K-major ("k is contiguous in global memory"), one box of X rows by 16 k-values:
 //      byte(x,k) = x*128 + (((k>>1) ^ (x&7)) << 4) + (k&1)*8
+//
+// Complex (ZGEMM) uses the real embedding  [Cr;Ci] = A' * B^  with
+//      A'[(i,d)][(l,c)] = +-component(d^c) of op(A)[i][l]   (2m x 2k),   B^[(l,c)][j] = component c of op(B)[l][j]
+// so a CTA tile is 128 real rows (64 complex rows of C) x 128 columns and a stage spans 16 real = 8 complex k.
+// The A' entries are gathered on the fly from the interleaved (re,im) tile by address arithmetic plus a sign
+// flip (integer XOR on the high word): 4 real FMA per complex FMA, no wasted DMMA work.
 enum Layout { MN_MAJOR = 0, K_MAJOR = 1 };
+enum Op { OP_N = 0, OP_T = 1, OP_C = 2 };
 
 // k permutation: MMA step j (0..3) of a 16-wide k block, thread column t = lane%4 handles
 //   k = (t0^j0) | t0<<1 | t1<<2 | (t1^j1)<<3.
@@ -68,23 +74,46 @@ __device__ __forceinline__ int kperm(int t, int j) {
     return (t0 ^ j0) | (t0 << 1) | (t1 << 2) | ((t1 ^ j1) << 3);
 }
 
-template <int LAYOUT>
-__device__ __forceinline__ uint32_t frag_offset(int idx, int g, int kk) {
-    if (LAYOUT == MN_MAJOR) {
-        const int xx = ((idx & 1) << 3) | g;
-        return (idx >> 1) * 2048 + kk * 128 + ((((xx >> 1) ^ (kk & 7))) << 4) + ((xx & 1) << 3);
+__device__ __forceinline__ uint32_t off_mn(int x, int k, int rows_per_box) {
+    return (x >> 4) * (rows_per_box * 128) + k * 128 + (((((x & 15) >> 1) ^ (k & 7))) << 4) + ((x & 1) << 3);
+}
+__device__ __forceinline__ uint32_t off_k(int x, int k) {
+    return x * 128 + ((((k >> 1) ^ (x & 7))) << 4) + ((k & 1) << 3);
+}
+
+// byte offset (inside the A slot of a stage) of the value feeding MMA column m' = idx*8+g at contraction index kk
+template <int OPA, bool CPLX>
+__device__ __forceinline__ uint32_t a_frag_offset(int idx, int g, int kk) {
+    if (!CPLX) {
+        return OPA == OP_N ? off_mn(idx * 8 + g, kk, 16) : off_k(idx * 8 + g, kk);
     } else {
-        const int x = idx * 8 + g;
-        return x * 128 + ((((kk >> 1) ^ g)) << 4) + ((kk & 1) << 3);
+        const int c = kk & 1, d = g & 1, l = kk >> 1;
+        if (OPA == OP_N) return off_mn((idx * 8 + g) ^ c, l, 8);  // real row (i, d^c), complex column l
+        return off_k(idx * 4 + (g >> 1), kk ^ d);                  // complex row i, real k index (l, d^c)
+    }
+}
+// same for the B slot, MMA row n = idx*8+g
+template <int OPB, bool CPLX>
+__device__ __forceinline__ uint32_t b_frag_offset(int idx, int g, int kk) {
+    if (!CPLX) {
+        return OPB == OP_N ? off_k(idx * 8 + g, kk) : off_mn(idx * 8 + g, kk, 16);
+    } else {
+        if (OPB == OP_N) return off_k(idx * 8 + g, kk);            // real k index (l,c), column j
+        return off_mn(2 * (idx * 8 + g) + (kk & 1), kk >> 1, 8);   // real row (j,c), complex column l
     }
 }
 
+__device__ __forceinline__ double flip_sign(double v, uint32_t mask) {
+    return __hiloint2double(__double2hiint(v) ^ static_cast<int>(mask), __double2loint(v));
+}
+
 struct GemmParams {
-    int64_t m, n, k;
-    double alpha, beta;
+    int64_t m, n, k;      // logical sizes (complex elements for ZGEMM)
+    double alpha[2], beta[2];
     double* C;
-    int64_t ldc;
+    int64_t ldc;          // in elements (complex elements for ZGEMM)
     int tiles_m, tiles_n;
+    int num_kb;
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -99,10 +128,15 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
     tm = band * G + rem % rows_in_band;
 }
 
-template <int LAYOUT_A, int LAYOUT_B>
+template <int OPA, int OPB, bool CPLX>
 __global__ void __launch_bounds__(THREADS, 1)
-dgemm_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   const GemmParams p) {
+gemm_f64_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const GemmParams p) {
+    constexpr int LAYOUT_A = (OPA == OP_N) ? MN_MAJOR : K_MAJOR;
+    constexpr int LAYOUT_B = (OPB == OP_N) ? K_MAJOR : MN_MAJOR;
+    constexpr int A_BYTES = CPLX ? OPERAND_STAGE_BYTES / 2 : OPERAND_STAGE_BYTES;
+    constexpr int TX_BYTES = A_BYTES + OPERAND_STAGE_BYTES;
+
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B needs 1024-byte aligned boxes
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,7 +156,7 @@ dgemm_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     __syncthreads();
 
     const int num_tiles = p.tiles_m * p.tiles_n;
-    const int num_kb = static_cast<int>((p.k + BK - 1) / BK);
+    const int num_kb = p.num_kb;
 
     if (warp >= CONSUMER_WARPS) {
         // ===== producer warpgroup: give registers back, warp 8 lane 0 drives TMA =====
@@ -134,26 +168,42 @@ dgemm_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int tm, tn;
                 tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-                const int m0 = tm * BM, n0 = tn * BN;
+                const int m0 = tm * BM, n0 = tn * BN;  // m0 in real rows (2 per complex row)
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + OPERAND_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    const int k0 = kb * BK;
-                    if (LAYOUT_A == MN_MAJOR) {
+                    mbar_arrive_expect_tx(&full_bar[s], TX_BYTES);
+                    const int k0 = kb * BK;  // real k units
+                    if (!CPLX) {
+                        if (LAYOUT_A == MN_MAJOR) {
 #pragma unroll
-                        for (int b = 0; b < BM / 16; ++b) tma_load_2d(sa + b * 2048, &map_a, &full_bar[s], m0 + 16 * b, k0);
-                    } else {
-                        tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
-                    }
-                    if (LAYOUT_B == MN_MAJOR) {
+                            for (int b = 0; b < BM / 16; ++b) tma_load_2d(sa + b * 2048, &map_a, &full_bar[s], m0 + 16 * b, k0);
+                        } else {
+                            tma_load_2d(sa, &map_a, &full_bar[s], k0, m0);
+                        }
+                        if (LAYOUT_B == MN_MAJOR) {
 #pragma unroll
-                        for (int b = 0; b < BN / 16; ++b) tma_load_2d(sb + b * 2048, &map_b, &full_bar[s], n0 + 16 * b, k0);
+                            for (int b = 0; b < BN / 16; ++b) tma_load_2d(sb + b * 2048, &map_b, &full_bar[s], n0 + 16 * b, k0);
+                        } else {
+                            tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+                        }
                     } else {
-                        tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+                        if (LAYOUT_A == MN_MAJOR) {  // real view (2m) x k, boxes {16, 8}
+#pragma unroll
+                            for (int b = 0; b < BM / 16; ++b) tma_load_2d(sa + b * 1024, &map_a, &full_bar[s], m0 + 16 * b, k0 / 2);
+                        } else {                     // real view (2k) x m, box {16, 64}
+                            tma_load_2d(sa, &map_a, &full_bar[s], k0, m0 / 2);
+                        }
+                        if (LAYOUT_B == MN_MAJOR) {  // real view (2n) x k, 16 boxes {16, 8}
+#pragma unroll
+                            for (int b = 0; b < 2 * BN / 16; ++b)
+                                tma_load_2d(sb + b * 1024, &map_b, &full_bar[s], 2 * n0 + 16 * b, k0 / 2);
+                        } else {                     // real view (2k) x n, box {16, 128}
+                            tma_load_2d(sb, &map_b, &full_bar[s], k0, n0);
+                        }
                     }
                 }
             }
@@ -167,10 +217,20 @@ dgemm_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int t = lane & 3;
     const int wm = warp % WARPS_M;
     const int wn = warp / WARPS_M;
-
-    // per-thread fragment byte offsets inside an operand stage buffer, for each k step j
-    // (idx-dependent parts are compile-time after unrolling)
     const uint32_t smem_base = smem_u32(smem);
+
+    // complex sign masks, indexed by the parity of the k step j (c = (t&1) ^ (j&1))
+    uint32_t sign_a[2] = {0u, 0u}, sign_b[2] = {0u, 0u};
+    if (CPLX) {
+#pragma unroll
+        for (int j0 = 0; j0 < 2; ++j0) {
+            const int c = (t & 1) ^ j0, d = g & 1;
+            // imaginary part is selected when d^c == 1; it enters Cr with -1 (d == 0), Ci with +1; conj flips it
+            const bool neg_a = ((d ^ c) == 1) && ((d == 0) != (OPA == OP_C));
+            sign_a[j0] = neg_a ? 0x80000000u : 0u;
+            sign_b[j0] = (OPB == OP_C && c == 1) ? 0x80000000u : 0u;
+        }
+    }
 
     double acc[NI][MI][2];
     uint32_t it = 0;
@@ -191,18 +251,30 @@ dgemm_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
             double fa[2][MI], fb[2][NI];
 #pragma unroll
-            for (int mi = 0; mi < MI; ++mi) fa[0][mi] = lds_f64(sa + frag_offset<LAYOUT_A>(wm * MI + mi, g, kperm(t, 0)));
+            for (int mi = 0; mi < MI; ++mi) {
+                fa[0][mi] = lds_f64(sa + a_frag_offset<OPA, CPLX>(wm * MI + mi, g, kperm(t, 0)));
+                if (CPLX) fa[0][mi] = flip_sign(fa[0][mi], sign_a[0]);
+            }
 #pragma unroll
-            for (int ni = 0; ni < NI; ++ni) fb[0][ni] = lds_f64(sb + frag_offset<LAYOUT_B>(wn * NI + ni, g, kperm(t, 0)));
+            for (int ni = 0; ni < NI; ++ni) {
+                fb[0][ni] = lds_f64(sb + b_frag_offset<OPB, CPLX>(wn * NI + ni, g, kperm(t, 0)));
+                if (CPLX && OPB == OP_C) fb[0][ni] = flip_sign(fb[0][ni], sign_b[0]);
+            }
 #pragma unroll
             for (int j = 0; j < BK / 4; ++j) {
                 const int cur = j & 1, nxt = cur ^ 1;
                 if (j + 1 < BK / 4) {
                     const int kk = kperm(t, j + 1);
 #pragma unroll
-                    for (int mi = 0; mi < MI; ++mi) fa[nxt][mi] = lds_f64(sa + frag_offset<LAYOUT_A>(wm * MI + mi, g, kk));
+                    for (int mi = 0; mi < MI; ++mi) {
+                        fa[nxt][mi] = lds_f64(sa + a_frag_offset<OPA, CPLX>(wm * MI + mi, g, kk));
+                        if (CPLX) fa[nxt][mi] = flip_sign(fa[nxt][mi], sign_a[(j + 1) & 1]);
+                    }
 #pragma unroll
-                    for (int ni = 0; ni < NI; ++ni) fb[nxt][ni] = lds_f64(sb + frag_offset<LAYOUT_B>(wn * NI + ni, g, kk));
+                    for (int ni = 0; ni < NI; ++ni) {
+                        fb[nxt][ni] = lds_f64(sb + b_frag_offset<OPB, CPLX>(wn * NI + ni, g, kk));
+                        if (CPLX && OPB == OP_C) fb[nxt][ni] = flip_sign(fb[nxt][ni], sign_b[(j + 1) & 1]);
+                    }
                 }
 #pragma unroll
                 for (int ni = 0; ni < NI; ++ni)
@@ -213,37 +285,69 @@ dgemm_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
 
-        // ===== epilogue: C = alpha*acc + beta*C, 16-byte accesses along m =====
-        const int64_t mbase = int64_t(tm) * BM + wm * WM + 2 * t;
+        // ===== epilogue: C = alpha*acc + beta*C; each thread owns pairs adjacent in column-major C =====
         const int64_t nbase = int64_t(tn) * BN + wn * WN + g;
-        const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        if (!CPLX) {
+            const double alpha = p.alpha[0], beta = p.beta[0];
+            const int64_t mbase = int64_t(tm) * BM + wm * WM + 2 * t;
+            const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) {
-            const int64_t nn = nbase + ni * 8;
-            if (nn >= p.n) continue;
-            double* ccol = p.C + nn * p.ldc;
+            for (int ni = 0; ni < NI; ++ni) {
+                const int64_t nn = nbase + ni * 8;
+                if (nn >= p.n) continue;
+                double* ccol = p.C + nn * p.ldc;
 #pragma unroll
-            for (int mi = 0; mi < MI; ++mi) {
-                const int64_t mm = mbase + mi * 8;
-                double v0 = p.alpha * acc[ni][mi][0];
-                double v1 = p.alpha * acc[ni][mi][1];
-                if (mm + 1 < p.m && vec_ok) {
-                    double2* ptr = reinterpret_cast<double2*>(ccol + mm);
-                    if (p.beta != 0.0) {
-                        const double2 old = *ptr;
-                        v0 += p.beta * old.x;
-                        v1 += p.beta * old.y;
+                for (int mi = 0; mi < MI; ++mi) {
+                    const int64_t mm = mbase + mi * 8;
+                    double v0 = alpha * acc[ni][mi][0];
+                    double v1 = alpha * acc[ni][mi][1];
+                    if (mm + 1 < p.m && vec_ok) {
+                        double2* ptr = reinterpret_cast<double2*>(ccol + mm);
+                        if (beta != 0.0) {
+                            const double2 old = *ptr;
+                            v0 += beta * old.x;
+                            v1 += beta * old.y;
+                        }
+                        *ptr = make_double2(v0, v1);
+                    } else {
+                        if (mm < p.m) {
+                            if (beta != 0.0) v0 += beta * ccol[mm];
+                            ccol[mm] = v0;
+                        }
+                        if (mm + 1 < p.m) {
+                            if (beta != 0.0) v1 += beta * ccol[mm + 1];
+                            ccol[mm + 1] = v1;
+                        }
                     }
-                    *ptr = make_double2(v0, v1);
-                } else {
-                    if (mm < p.m) {
-                        if (p.beta != 0.0) v0 += p.beta * ccol[mm];
-                        ccol[mm] = v0;
+                }
+            }
+        } else {
+            const double ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
+            const bool beta_zero = (br == 0.0 && bi == 0.0);
+            const int64_t ibase = int64_t(tm) * (BM / 2) + wm * (WM / 2) + t;  // complex row
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+#pragma unroll
+            for (int ni = 0; ni < NI; ++ni) {
+                const int64_t nn = nbase + ni * 8;
+                if (nn >= p.n) continue;
+                double* ccol = p.C + 2 * nn * p.ldc;
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) {
+                    const int64_t ii = ibase + mi * 4;
+                    if (ii >= p.m) continue;
+                    const double xr = acc[ni][mi][0], xi = acc[ni][mi][1];
+                    double vr = ar * xr - ai * xi;
+                    double vi = ar * xi + ai * xr;
+                    double* ptr = ccol + 2 * ii;
+                    if (!beta_zero) {
+                        double cr, ci;
+                        if (vec_ok) { const double2 old = *reinterpret_cast<double2*>(ptr); cr = old.x; ci = old.y; }
+                        else { cr = ptr[0]; ci = ptr[1]; }
+                        vr += br * cr - bi * ci;
+                        vi += br * ci + bi * cr;
                     }
-                    if (mm + 1 < p.m) {
-                        if (p.beta != 0.0) v1 += p.beta * ccol[mm + 1];
-                        ccol[mm + 1] = v1;
-                    }
+                    if (vec_ok) *reinterpret_cast<double2*>(ptr) = make_double2(vr, vi);
+                    else { ptr[0] = vr; ptr[1] = vi; }
                 }
             }
         }
@@ -311,12 +415,45 @@ __global__ void __launch_bounds__(256) dgemm_generic_kernel(int ta, int tb, int6
     }
 }
 
-__global__ void scale_matrix_kernel(int64_t m, int64_t n, double beta, double* C, int64_t ldc) {
+template <bool CPLX>
+__global__ void scale_matrix_kernel(int64_t m, int64_t n, double br, double bi, double* C, int64_t ldc) {
     const int64_t total = m * n;
     for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        double* ptr = C + (i % m) + (i / m) * ldc;
-        *ptr = (beta == 0.0) ? 0.0 : beta * *ptr;
+        if (!CPLX) {
+            double* ptr = C + (i % m) + (i / m) * ldc;
+            *ptr = (br == 0.0) ? 0.0 : br * *ptr;
+        } else {
+            double* ptr = C + 2 * ((i % m) + (i / m) * ldc);
+            if (br == 0.0 && bi == 0.0) { ptr[0] = 0.0; ptr[1] = 0.0; }
+            else { const double cr = ptr[0], ci = ptr[1]; ptr[0] = br * cr - bi * ci; ptr[1] = br * ci + bi * cr; }
+        }
     }
+}
+
+// complex generic path (only reached with a 16-byte-misaligned base pointer): one thread per C element
+__global__ void zgemm_generic_kernel(int oa, int ob, int64_t m, int64_t n, int64_t k, double ar, double ai,
+                                     const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                                     double br, double bi, double* __restrict__ C, int64_t ldc) {
+    const int64_t i = blockIdx.x * int64_t(16) + threadIdx.x, j = blockIdx.y * int64_t(16) + threadIdx.y;
+    if (i >= m || j >= n) return;
+    double sr = 0.0, si = 0.0;
+    for (int64_t l = 0; l < k; ++l) {
+        const double* a = A + 2 * (oa == OP_N ? i + l * lda : l + i * lda);
+        const double* b = B + 2 * (ob == OP_N ? l + j * ldb : j + l * ldb);
+        const double xr = a[0], xi = (oa == OP_C) ? -a[1] : a[1];
+        const double yr = b[0], yi = (ob == OP_C) ? -b[1] : b[1];
+        sr += xr * yr - xi * yi;
+        si += xr * yi + xi * yr;
+    }
+    double vr = ar * sr - ai * si, vi = ar * si + ai * sr;
+    double* c = C + 2 * (i + j * ldc);
+    if (!(br == 0.0 && bi == 0.0)) {
+        const double cr = c[0], ci = c[1];
+        vr += br * cr - bi * ci;
+        vi += br * ci + bi * cr;
+    }
+    c[0] = vr;
+    c[1] = vi;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -353,9 +490,9 @@ bool make_map(CUtensorMap* map, const double* base, int64_t d0, int64_t d1, int6
     return r == CUDA_SUCCESS;
 }
 
-template <int LA, int LB>
+template <int OPA, int OPB, bool CPLX>
 cudaError_t launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int sms, cudaStream_t stream) {
-    auto kern = dgemm_sm100_kernel<LA, LB>;
+    auto kern = gemm_f64_sm100_kernel<OPA, OPB, CPLX>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -366,6 +503,24 @@ cudaError_t launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
     const int grid = tiles < sms ? tiles : sms;
     kern<<<grid, THREADS, SMEM_BYTES, stream>>>(ma, mb, p);
     return cudaGetLastError();
+}
+
+template <bool CPLX>
+cudaError_t dispatch_tma(int oa, int ob, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int sms,
+                         cudaStream_t st) {
+    if (!CPLX) {  // real: 'C' == 'T'
+        oa = oa ? OP_T : OP_N;
+        ob = ob ? OP_T : OP_N;
+    }
+#define COSMA_B200_CASE(A_, B_) \
+    if (oa == A_ && ob == B_) return launch_tma<A_, B_, CPLX>(ma, mb, p, sms, st);
+    COSMA_B200_CASE(OP_N, OP_N) COSMA_B200_CASE(OP_N, OP_T) COSMA_B200_CASE(OP_T, OP_N) COSMA_B200_CASE(OP_T, OP_T)
+    if constexpr (CPLX) {
+        COSMA_B200_CASE(OP_N, OP_C) COSMA_B200_CASE(OP_T, OP_C) COSMA_B200_CASE(OP_C, OP_N) COSMA_B200_CASE(OP_C, OP_T)
+        COSMA_B200_CASE(OP_C, OP_C)
+    }
+#undef COSMA_B200_CASE
+    return cudaErrorInvalidValue;
 }
 
 int device_sm_count() {
@@ -380,58 +535,94 @@ int device_sm_count() {
 
 }  // namespace
 
-int dgemm_sm100(cudaStream_t stream, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
-                const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
-                int* path_used) {
-    const bool ta = !(transa == 'N' || transa == 'n');
-    const bool tb = !(transb == 'N' || transb == 'n');
-    if (m < 0 || n < 0 || k < 0) return COSMA_B200_INVALID_ARG;
-    if (lda < (ta ? (k > 1 ? k : 1) : (m > 1 ? m : 1)) || ldb < (tb ? (n > 1 ? n : 1) : (k > 1 ? k : 1)) ||
-        ldc < (m > 1 ? m : 1))
-        return COSMA_B200_INVALID_ARG;
-    if (m == 0 || n == 0) return COSMA_B200_OK;
+static int parse_op(char c) {
+    switch (c) {
+        case 'N': case 'n': return OP_N;
+        case 'T': case 't': return OP_T;
+        case 'C': case 'c': return OP_C;
+        default: return -1;
+    }
+}
+
+// CPLX == false: double; CPLX == true: complex<double> as interleaved doubles (sizes/lds in complex elements)
+template <bool CPLX>
+static int gemm_f64_impl(cudaStream_t stream, char transa, char transb, int64_t m, int64_t n, int64_t k,
+                         const double* alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                         const double* beta, double* C, int64_t ldc, int* path_used) {
+    const int oa = parse_op(transa), ob = parse_op(transb);
+    if (oa < 0 || ob < 0 || m < 0 || n < 0 || k < 0) return COSMA_B200_INVALID_ARG;
+    const bool ta = oa != OP_N, tb = ob != OP_N;
+    auto max1 = [](int64_t v) { return v > 1 ? v : int64_t(1); };
+    if (lda < max1(ta ? k : m) || ldb < max1(tb ? n : k) || ldc < max1(m)) return COSMA_B200_INVALID_ARG;
     if (path_used) *path_used = 0;
-    if (k == 0 || alpha == 0.0) {
+    if (m == 0 || n == 0) return COSMA_B200_OK;
+    constexpr int E = CPLX ? 2 : 1;  // doubles per element
+    const bool alpha_zero = alpha[0] == 0.0 && (!CPLX || alpha[1] == 0.0);
+    if (k == 0 || alpha_zero) {
         // BLAS semantics: C = beta*C (C not read when beta == 0)
-        if (beta != 1.0) {
-            scale_matrix_kernel<<<device_sm_count() * 4, 256, 0, stream>>>(m, n, beta, C, ldc);
+        const bool beta_one = beta[0] == 1.0 && (!CPLX || beta[1] == 0.0);
+        if (!beta_one) {
+            scale_matrix_kernel<CPLX><<<device_sm_count() * 4, 256, 0, stream>>>(m, n, beta[0], CPLX ? beta[1] : 0.0, C, ldc);
             if (cudaGetLastError() != cudaSuccess) return COSMA_B200_CUDA_ERROR;
         }
         return COSMA_B200_OK;
     }
-    const bool aligned = ((lda & 1) == 0) && ((ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+    const bool aligned = (CPLX || (((lda & 1) == 0) && ((ldb & 1) == 0))) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
     if (aligned) {
         CUtensorMap ma, mb;
         bool ok;
-        // A: 'N' -> stored m x k (m contiguous) MN-major; 'T' -> stored k x m (k contiguous) K-major
-        ok = ta ? make_map(&ma, A, k, m, lda, 16, BM) : make_map(&ma, A, m, k, lda, 16, BK);
-        // B: 'N' -> stored k x n (k contiguous) K-major; 'T' -> stored n x k (n contiguous) MN-major
-        ok = ok && (tb ? make_map(&mb, B, n, k, ldb, 16, BK) : make_map(&mb, B, k, n, ldb, 16, BN));
+        if (!CPLX) {
+            // A: 'N' -> stored m x k (m contiguous) MN-major; 'T' -> stored k x m (k contiguous) K-major
+            ok = ta ? make_map(&ma, A, k, m, lda, 16, BM) : make_map(&ma, A, m, k, lda, 16, BK);
+            // B: 'N' -> stored k x n (k contiguous) K-major; 'T' -> stored n x k (n contiguous) MN-major
+            ok = ok && (tb ? make_map(&mb, B, n, k, ldb, 16, BK) : make_map(&mb, B, k, n, ldb, 16, BN));
+        } else {
+            // real views of the interleaved complex matrices: contiguous extent doubles, leading dimension doubles
+            ok = ta ? make_map(&ma, A, 2 * k, m, 2 * lda, 16, BM / 2) : make_map(&ma, A, 2 * m, k, 2 * lda, 16, BK / 2);
+            ok = ok && (tb ? make_map(&mb, B, 2 * n, k, 2 * ldb, 16, BK / 2) : make_map(&mb, B, 2 * k, n, 2 * ldb, 16, BN));
+        }
         if (ok) {
             GemmParams p;
-            p.m = m; p.n = n; p.k = k; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc;
-            p.tiles_m = static_cast<int>((m + BM - 1) / BM);
+            p.m = m; p.n = n; p.k = k;
+            p.alpha[0] = alpha[0]; p.alpha[1] = CPLX ? alpha[1] : 0.0;
+            p.beta[0] = beta[0]; p.beta[1] = CPLX ? beta[1] : 0.0;
+            p.C = C; p.ldc = ldc;
+            p.tiles_m = static_cast<int>((E * m + BM - 1) / BM);
             p.tiles_n = static_cast<int>((n + BN - 1) / BN);
-            const int sms = device_sm_count();
-            cudaError_t e;
-            if (!ta && !tb) e = launch_tma<MN_MAJOR, K_MAJOR>(ma, mb, p, sms, stream);
-            else if (!ta && tb) e = launch_tma<MN_MAJOR, MN_MAJOR>(ma, mb, p, sms, stream);
-            else if (ta && !tb) e = launch_tma<K_MAJOR, K_MAJOR>(ma, mb, p, sms, stream);
-            else e = launch_tma<K_MAJOR, MN_MAJOR>(ma, mb, p, sms, stream);
+            p.num_kb = static_cast<int>((E * k + BK - 1) / BK);
+            cudaError_t e = dispatch_tma<CPLX>(oa, ob, ma, mb, p, device_sm_count(), stream);
             if (e != cudaSuccess) {
-                fprintf(stderr, "cosma_b200: dgemm_sm100 launch failed: %s\n", cudaGetErrorString(e));
+                fprintf(stderr, "cosma_b200: gemm_f64_sm100 launch failed: %s\n", cudaGetErrorString(e));
                 return COSMA_B200_CUDA_ERROR;
             }
             if (path_used) *path_used = 1;
             return COSMA_B200_OK;
         }
     }
-    dim3 grid(static_cast<unsigned>((m + GT - 1) / GT), static_cast<unsigned>((n + GT - 1) / GT));
-    dgemm_generic_kernel<<<grid, 256, 0, stream>>>(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!CPLX) {
+        dim3 grid(static_cast<unsigned>((m + GT - 1) / GT), static_cast<unsigned>((n + GT - 1) / GT));
+        dgemm_generic_kernel<<<grid, 256, 0, stream>>>(ta, tb, m, n, k, alpha[0], A, lda, B, ldb, beta[0], C, ldc);
+    } else {
+        dim3 grid(static_cast<unsigned>((m + 15) / 16), static_cast<unsigned>((n + 15) / 16));
+        zgemm_generic_kernel<<<grid, dim3(16, 16), 0, stream>>>(oa, ob, m, n, k, alpha[0], alpha[1], A, lda, B, ldb, beta[0],
+                                                                 beta[1], C, ldc);
+    }
     if (cudaGetLastError() != cudaSuccess) return COSMA_B200_CUDA_ERROR;
     if (path_used) *path_used = 2;
     return COSMA_B200_OK;
+}
+
+int dgemm_sm100(cudaStream_t stream, char transa, char transb, int64_t m, int64_t n, int64_t k, double alpha,
+                const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                int* path_used) {
+    return gemm_f64_impl<false>(stream, transa, transb, m, n, k, &alpha, A, lda, B, ldb, &beta, C, ldc, path_used);
+}
+
+int zgemm_sm100(cudaStream_t stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const double* alpha,
+                const double* A, int64_t lda, const double* B, int64_t ldb, const double* beta, double* C, int64_t ldc,
+                int* path_used) {
+    return gemm_f64_impl<true>(stream, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, path_used);
 }
 
 }  // namespace cosma_b200

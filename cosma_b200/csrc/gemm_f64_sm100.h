@@ -12,4 +12,8 @@ int dgemm_sm100(cudaStream_t stream, char transa, char transb, int64_t m, int64_
                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
                 int* path_used);
 
+int zgemm_sm100(cudaStream_t stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const double* alpha,
+                const double* A, int64_t lda, const double* B, int64_t ldb, const double* beta, double* C, int64_t ldc,
+                int* path_used);
+
 }  // namespace cosma_b200

@@ -1,0 +1,149 @@
+"""GPU parity of the local GEMM (K1 DGEMM, K2 ZGEMM) through the C ABI against the oracle
+(oracle/gemm_oracle.c restating local_multiply_cpu, reference src/cosma/local_multiply.cpp:277-297).
+
+Tolerance (north_star): normwise ||C - C_ref||_F / ||C_ref||_F <= 1e-13 for FP64 / complex128; integer-valued
+inputs (Tiled-MM convention, libs/Tiled-MM/tests/test-multiply.cpp:60-68) must be bit-exact. The reference's own
+element-wise criterion (utils/cosma_utils.hpp:366-377, rel err < 1e-8) is checked too."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-13
+
+
+def _dev(a):
+    return torch.from_numpy(a).cuda()
+
+
+def _run(oracle, dtype, ta, tb, m, n, k, alpha, beta, pad=0, ints=False, seed=0, nan_c=None):
+    from cosma_b200 import gemm, _lib
+    rng = np.random.default_rng(seed)
+    cplx = dtype == "z"
+    npdt = np.complex128 if cplx else np.float64
+    ar, ac = (k, m) if ta != "N" else (m, k)
+    br, bc = (n, k) if tb != "N" else (k, n)
+    lda, ldb, ldc = max(1, ar + pad), max(1, br + pad), max(1, m + pad)
+
+    def fill(rows, cols, ld):
+        cnt = max(1, ld * cols)
+        if ints:
+            v = rng.integers(0, 10, size=cnt).astype(np.float64)
+            if cplx:
+                v = v + 1j * rng.integers(0, 10, size=cnt)
+        else:
+            v = rng.random(cnt) * 10  # U[0,10) like the reference miniapp (miniapp/cosma_miniapp.cpp:21-25)
+            if cplx:
+                v = v + 1j * rng.random(cnt) * 10
+        return v.astype(npdt)
+
+    A, B, C = fill(ar, ac, lda), fill(br, bc, ldb), fill(m, n, ldc)
+    if nan_c if nan_c is not None else (beta == 0):
+        C[:] = np.nan  # beta == 0 must not read C (utils/pxgemm_utils.hpp:603-637)
+    want = oracle.gemm(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C.copy(), ldc)
+    dA, dB, dC = _dev(A), _dev(B), _dev(C)
+    gemm.gemm_raw(dtype, ta, tb, m, n, k, alpha, dA.data_ptr(), lda, dB.data_ptr(), ldb, beta, dC.data_ptr(), ldc)
+    torch.cuda.synchronize()
+    got = dC.cpu().numpy()
+    path = _lib.load().cosma_b200_last_gemm_path()
+    # compare only the m x n window (padding rows must be untouched)
+    W = lambda v: v[:ldc * n].reshape(n, ldc)[:, :m] if n and m else v[:0]
+    g, w = W(got), W(want)
+    if pad and n:
+        assert np.array_equal(got[:ldc * n].reshape(n, ldc)[:, m:], C[:ldc * n].reshape(n, ldc)[:, m:], equal_nan=True)
+    assert not np.isnan(g).any()
+    if ints:
+        assert np.array_equal(g, w)
+    elif w.size:
+        err = np.linalg.norm(g - w) / max(np.linalg.norm(w), 1e-300)
+        assert err <= TOL, err
+        assert np.all(np.abs(g - w) <= 1e-8 * np.abs(w) + 1e-300)
+    return path
+
+
+@pytest.mark.parametrize("ta", ["N", "T"])
+@pytest.mark.parametrize("tb", ["N", "T"])
+@pytest.mark.parametrize("m,n,k,alpha,beta,pad", [
+    (128, 128, 16, 1.0, 0.0, 0), (256, 256, 64, 1.0, 1.0, 0), (300, 200, 100, 1.0, 1.0, 0),
+    (130, 70, 18, 2.5, -0.5, 2), (1, 1, 1, 1.0, 0.0, 0), (2, 3, 5, 1.0, 1.0, 0), (513, 257, 129, -1.0, 0.5, 1),
+])
+def test_dgemm_vs_oracle(oracle, ta, tb, m, n, k, alpha, beta, pad):
+    _run(oracle, "d", ta, tb, m, n, k, alpha, beta, pad=pad)
+
+
+@pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")])
+def test_dgemm_integer_exact(oracle, ta, tb):
+    assert _run(oracle, "d", ta, tb, 384, 272, 200, 1.0, 1.0, ints=True) == 1
+
+
+def test_dgemm_reference_correctness_case(oracle):
+    # BASELINE configs[0]: square dgemm 2000^3 with strategy pk2 -> base case 2000 x 2000 x 1000, alpha=1, beta=0/1
+    _run(oracle, "d", "N", "N", 2000, 2000, 1000, 1.0, 0.0, ints=True)
+
+
+def test_dgemm_generic_path_odd_ld(oracle):
+    assert _run(oracle, "d", "N", "N", 127, 129, 33, 1.0, 1.0, pad=0) == 2  # lda = 127 is odd -> no TMA
+    assert _run(oracle, "d", "T", "T", 65, 63, 17, 1.5, 0.0) == 2
+
+
+@pytest.mark.parametrize("m,n,k", [(0, 5, 3), (5, 0, 3), (5, 3, 0)])
+def test_dgemm_degenerate(oracle, m, n, k):
+    _run(oracle, "d", "N", "N", m, n, k, 1.0, 2.0, nan_c=False)
+
+
+def test_dgemm_alpha_zero_beta_zero_clears_nan(oracle):
+    _run(oracle, "d", "N", "N", 64, 64, 64, 0.0, 0.0)
+
+
+@pytest.mark.parametrize("ta", ["N", "T", "C"])
+@pytest.mark.parametrize("tb", ["N", "T", "C"])
+@pytest.mark.parametrize("m,n,k,alpha,beta,pad", [
+    (64, 128, 8, 1.0, 0.0, 0), (100, 90, 70, 1.0, 1.0, 0), (65, 33, 19, 0.7 - 0.2j, 0.3 + 0.4j, 3), (1, 1, 1, 1j, 0.0, 0),
+])
+def test_zgemm_vs_oracle(oracle, ta, tb, m, n, k, alpha, beta, pad):
+    assert _run(oracle, "z", ta, tb, m, n, k, alpha, beta, pad=pad) == 1
+
+
+@pytest.mark.parametrize("ta,tb", [("N", "N"), ("C", "N"), ("N", "C"), ("T", "T")])
+def test_zgemm_integer_exact(oracle, ta, tb):
+    _run(oracle, "z", ta, tb, 192, 136, 104, 1.0, 1.0, ints=True)
+
+
+def test_zgemm_degenerate(oracle):
+    _run(oracle, "z", "N", "N", 7, 5, 0, 1.0, 0.5 + 0.5j, nan_c=False)
+    _run(oracle, "z", "N", "N", 7, 5, 3, 0.0, 0.0)
+
+
+def test_invalid_arguments_are_rejected(oracle):
+    from cosma_b200 import gemm, CosmaB200Error
+    d = torch.zeros(16, dtype=torch.float64, device="cuda")
+    with pytest.raises(CosmaB200Error):
+        gemm.gemm_raw("d", "N", "N", 4, 4, 4, 1.0, d.data_ptr(), 2, d.data_ptr(), 4, 0.0, d.data_ptr(), 4)  # lda < m
+    with pytest.raises(CosmaB200Error):
+        gemm.gemm_raw("d", "X", "N", 4, 4, 4, 1.0, d.data_ptr(), 4, d.data_ptr(), 4, 0.0, d.data_ptr(), 4)
+
+
+def test_dgemm_full_size_properties():
+    """BASELINE configs[1] size (16384^3): size-independent checks -- linearity in alpha and exactness on
+    integer inputs against a row/column checksum identity  1^T (A B) 1 = (1^T A)(B 1)."""
+    from cosma_b200 import gemm
+    n = 16384
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    A = torch.randint(0, 10, (n * n,), device="cuda", generator=g).double()
+    B = torch.randint(0, 10, (n * n,), device="cuda", generator=g).double()
+    C = torch.full((n * n,), float("nan"), device="cuda", dtype=torch.float64)
+    gemm.gemm_raw("d", "N", "N", n, n, n, 1.0, A.data_ptr(), n, B.data_ptr(), n, 0.0, C.data_ptr(), n)
+    # column-major storage: A.view(k, m)[kk, i] = A(i, kk)
+    colsum_A = A.view(n, n).sum(dim=1)          # sum over i of A(i, kk) -> indexed by kk
+    rowsum_B = B.view(n, n).sum(dim=0)          # sum over j of B(kk, j) -> indexed by kk
+    want_total = (colsum_A * rowsum_B).sum()
+    got_total = C.sum()
+    assert not torch.isnan(C).any()
+    assert got_total.item() == want_total.item()  # all integers < 2^53: exact
+    # per-column checksum:  1^T C[:, j] = (1^T A) B[:, j]
+    col_check = torch.mv(B.view(n, n), colsum_A)      # for each j: sum_kk B(kk, j) * colsum_A[kk]
+    assert torch.equal(C.view(n, n).sum(dim=1), col_check)
+    # linearity: alpha = 2, beta = 1 on top of the result gives 3x
+    gemm.gemm_raw("d", "N", "N", n, n, n, 2.0, A.data_ptr(), n, B.data_ptr(), n, 1.0, C.data_ptr(), n)
+    assert torch.equal(C.view(n, n).sum(dim=1), 3 * col_check)
