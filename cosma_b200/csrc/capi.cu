@@ -7,6 +7,7 @@
 namespace {
 thread_local std::string g_last_error;
 thread_local int g_last_gemm_path = 0;
+thread_local int g_last_launches = 0;
 }  // namespace
 
 namespace cosma_b200 {
@@ -34,5 +35,20 @@ int cosma_b200_zgemm(void* stream, char transa, char transb, int64_t m, int64_t 
     return cosma_b200::zgemm_sm100(static_cast<cudaStream_t>(stream), transa, transb, m, n, k, alpha, A, lda, B, ldb, beta,
                                    C, ldc, &g_last_gemm_path);
 }
+
+int cosma_b200_dgemm_host(void* stream, int64_t m, int64_t n, int64_t k, const double* alpha, const double* A, int64_t lda,
+                          const double* B, int64_t ldb, const double* beta, double* C, int64_t ldc) {
+    if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
+    return cosma_b200::gemm_f64_host(static_cast<cudaStream_t>(stream), 1, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
+                                     &g_last_launches);
+}
+int cosma_b200_zgemm_host(void* stream, int64_t m, int64_t n, int64_t k, const double* alpha, const double* A, int64_t lda,
+                          const double* B, int64_t ldb, const double* beta, double* C, int64_t ldc) {
+    if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
+    return cosma_b200::gemm_f64_host(static_cast<cudaStream_t>(stream), 2, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
+                                     &g_last_launches);
+}
+int cosma_b200_last_launch_count(void) { return g_last_launches; }
+void cosma_b200_release_workspace(void) { cosma_b200::release_host_gemm_workspace(); }
 
 }  // extern "C"

@@ -81,26 +81,38 @@ __device__ __forceinline__ uint32_t off_k(int x, int k) {
     return x * 128 + ((((k >> 1) ^ (x & 7))) << 4) + ((k & 1) << 3);
 }
 
-// byte offset (inside the A slot of a stage) of the value feeding MMA column m' = idx*8+g at contraction index kk
+// Fragment addressing, split into a per-thread runtime part (depends on lane and k step, hoisted out of all
+// loops) and a compile-time part (depends on the fragment index idx):
+//      offset(idx, g, kk) = (base(g, kk) ^ (xor64(idx) ? 64 : 0)) + stride(idx)
+// A slot: value feeding MMA column m' = idx*8+g at contraction index kk.
 template <int OPA, bool CPLX>
-__device__ __forceinline__ uint32_t a_frag_offset(int idx, int g, int kk) {
-    if (!CPLX) {
-        return OPA == OP_N ? off_mn(idx * 8 + g, kk, 16) : off_k(idx * 8 + g, kk);
-    } else {
-        const int c = kk & 1, d = g & 1, l = kk >> 1;
-        if (OPA == OP_N) return off_mn((idx * 8 + g) ^ c, l, 8);  // real row (i, d^c), complex column l
-        return off_k(idx * 4 + (g >> 1), kk ^ d);                  // complex row i, real k index (l, d^c)
-    }
+__device__ __forceinline__ uint32_t a_frag_base(int g, int kk) {
+    if (!CPLX) return OPA == OP_N ? off_mn(g, kk, 16) : off_k(g, kk);
+    const int c = kk & 1, d = g & 1;
+    if (OPA == OP_N) return off_mn(g ^ c, kk >> 1, 8);  // real row (i, d^c), complex column l
+    return off_k(g >> 1, kk ^ d);                       // complex row i, real k index (l, d^c)
 }
-// same for the B slot, MMA row n = idx*8+g
-template <int OPB, bool CPLX>
-__device__ __forceinline__ uint32_t b_frag_offset(int idx, int g, int kk) {
+// ab = stage address + base, abx = ab ^ 64 (stage addresses are 1024-byte aligned, so the xor commutes with the add)
+template <int OPA, bool CPLX>
+__device__ __forceinline__ uint32_t a_frag_addr(uint32_t ab, uint32_t abx, int idx) {
     if (!CPLX) {
-        return OPB == OP_N ? off_k(idx * 8 + g, kk) : off_mn(idx * 8 + g, kk, 16);
-    } else {
-        if (OPB == OP_N) return off_k(idx * 8 + g, kk);            // real k index (l,c), column j
-        return off_mn(2 * (idx * 8 + g) + (kk & 1), kk >> 1, 8);   // real row (j,c), complex column l
+        if (OPA == OP_N) return ((idx & 1) ? abx : ab) + (idx >> 1) * 2048;  // x = idx*8+g, 16-wide boxes
+        return ab + idx * 1024;                                              // row x = idx*8+g
     }
+    if (OPA == OP_N) return ((idx & 1) ? abx : ab) + (idx >> 1) * 1024;      // boxes of 8 k-rows
+    return ((idx & 1) ? abx : ab) + idx * 512;                               // row x = idx*4 + (g>>1)
+}
+// B slot: value feeding MMA row n = idx*8+g at contraction index kk.
+template <int OPB, bool CPLX>
+__device__ __forceinline__ uint32_t b_frag_base(int g, int kk) {
+    if (!CPLX) return OPB == OP_N ? off_k(g, kk) : off_mn(g, kk, 16);
+    if (OPB == OP_N) return off_k(g, kk);               // real k index (l,c), column j
+    return off_mn(2 * g + (kk & 1), kk >> 1, 8);        // real row (j,c), complex column l
+}
+template <int OPB, bool CPLX>
+__device__ __forceinline__ uint32_t b_frag_addr(uint32_t bb, uint32_t bbx, int idx) {
+    if (!CPLX && OPB != OP_N) return ((idx & 1) ? bbx : bb) + (idx >> 1) * 2048;
+    return bb + idx * 1024;  // K-major rows, or complex MN-major (x = idx*16 + 2g + c: one 8-row box per idx)
 }
 
 __device__ __forceinline__ double flip_sign(double v, uint32_t mask) {
@@ -232,7 +244,35 @@ gemm_f64_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
     }
 
+    // per-thread fragment address bases for the 4 k steps of a stage (hoisted out of every loop)
+    uint32_t a_base[BK / 4], b_base[BK / 4];
+#pragma unroll
+    for (int j = 0; j < BK / 4; ++j) {
+        // lane part + this warp's first fragment (wm*MI and wn*NI are even, so fragment parity is that of mi / ni)
+        a_base[j] = a_frag_base<OPA, CPLX>(g, kperm(t, j)) + a_frag_addr<OPA, CPLX>(0u, 0u, wm * MI);
+        b_base[j] = OPERAND_STAGE_BYTES + b_frag_base<OPB, CPLX>(g, kperm(t, j)) + b_frag_addr<OPB, CPLX>(0u, 0u, wn * NI);
+        // opaque to the optimiser: otherwise ptxas rematerialises the whole swizzle computation (from S2R tid)
+        // inside the k loop instead of keeping 8 registers live
+        asm volatile("" : "+r"(a_base[j]), "+r"(b_base[j]));
+    }
+
     double acc[NI][MI][2];
+    double fa[2][MI], fb[2][NI];
+    // loads the fragments of k step j of the stage at shared address `st` into buffer `buf`
+    auto load_frags = [&](uint32_t st, int j, int buf) {
+        const uint32_t ab = st + a_base[j], abx = ab ^ 64u, bb = st + b_base[j], bbx = bb ^ 64u;
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+            fa[buf][mi] = lds_f64(a_frag_addr<OPA, CPLX>(ab, abx, mi));
+            if (CPLX) fa[buf][mi] = flip_sign(fa[buf][mi], sign_a[j & 1]);
+        }
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+            fb[buf][ni] = lds_f64(b_frag_addr<OPB, CPLX>(bb, bbx, ni));
+            if (CPLX && OPB == OP_C) fb[buf][ni] = flip_sign(fb[buf][ni], sign_b[j & 1]);
+        }
+    };
+
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int tm, tn;
@@ -242,45 +282,30 @@ gemm_f64_sm100_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
             for (int mi = 0; mi < MI; ++mi) acc[ni][mi][0] = acc[ni][mi][1] = 0.0;
 
+        // software pipeline over (stage, k step): the fragments of step j+1 -- crossing into the next stage at
+        // j = 3 -- are in flight while the 32 DMMAs of step j issue, so a warp never sits at a stage boundary
+        // with an empty DMMA queue.
+        mbar_wait(&full_bar[it % STAGES], (it / STAGES) & 1);
+        load_frags(smem_base + (it % STAGES) * STAGE_BYTES, 0, 0);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
             const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&full_bar[s], ph);
-            const uint32_t sa = smem_base + s * STAGE_BYTES;
-            const uint32_t sb = sa + OPERAND_STAGE_BYTES;
-
-            double fa[2][MI], fb[2][NI];
-#pragma unroll
-            for (int mi = 0; mi < MI; ++mi) {
-                fa[0][mi] = lds_f64(sa + a_frag_offset<OPA, CPLX>(wm * MI + mi, g, kperm(t, 0)));
-                if (CPLX) fa[0][mi] = flip_sign(fa[0][mi], sign_a[0]);
-            }
-#pragma unroll
-            for (int ni = 0; ni < NI; ++ni) {
-                fb[0][ni] = lds_f64(sb + b_frag_offset<OPB, CPLX>(wn * NI + ni, g, kperm(t, 0)));
-                if (CPLX && OPB == OP_C) fb[0][ni] = flip_sign(fb[0][ni], sign_b[0]);
-            }
+            const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
             for (int j = 0; j < BK / 4; ++j) {
                 const int cur = j & 1, nxt = cur ^ 1;
                 if (j + 1 < BK / 4) {
-                    const int kk = kperm(t, j + 1);
-#pragma unroll
-                    for (int mi = 0; mi < MI; ++mi) {
-                        fa[nxt][mi] = lds_f64(sa + a_frag_offset<OPA, CPLX>(wm * MI + mi, g, kk));
-                        if (CPLX) fa[nxt][mi] = flip_sign(fa[nxt][mi], sign_a[(j + 1) & 1]);
-                    }
-#pragma unroll
-                    for (int ni = 0; ni < NI; ++ni) {
-                        fb[nxt][ni] = lds_f64(sb + b_frag_offset<OPB, CPLX>(wn * NI + ni, g, kk));
-                        if (CPLX && OPB == OP_C) fb[nxt][ni] = flip_sign(fb[nxt][ni], sign_b[(j + 1) & 1]);
-                    }
+                    load_frags(st, j + 1, nxt);
+                } else if (kb + 1 < num_kb) {
+                    const uint32_t itn = it + 1;
+                    mbar_wait(&full_bar[itn % STAGES], (itn / STAGES) & 1);
+                    load_frags(smem_base + (itn % STAGES) * STAGE_BYTES, 0, nxt);
                 }
 #pragma unroll
                 for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
                     for (int mi = 0; mi < MI; ++mi) dmma884(acc[ni][mi][0], acc[ni][mi][1], fb[cur][ni], fa[cur][mi]);
             }
+            // every fragment of stage s was consumed by an issued DMMA: hand the slot back to the producer
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }

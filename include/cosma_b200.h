@@ -53,6 +53,24 @@ COSMA_B200_API int cosma_b200_zgemm(void* stream, char transa, char transb, int6
 /* Which kernel the last ?gemm call on this thread used: 0 none, 1 TMA+DMMA persistent, 2 generic. */
 COSMA_B200_API int cosma_b200_last_gemm_path(void);
 
+/* ---- local GEMM with HOST operands ('N','N') -------------------------------------------------
+ * Same contract as the reference's GPU base case, which receives host pointers and streams tiles
+ * through the device (gpu::gemm, libs/Tiled-MM/src/Tiled-MM/tiled_mm.cpp:492-624; copy_c_back = true).
+ * A is uploaded once; column panels of B and C are pipelined (H2D / DMMA kernel / D2H overlap on three
+ * streams). Pinned host memory is required for the copies to be asynchronous. Work is ordered after
+ * everything already queued on `stream`, and `stream` completes when C is back in host memory.
+ */
+COSMA_B200_API int cosma_b200_dgemm_host(void* stream, int64_t m, int64_t n, int64_t k, const double* alpha, const double* A,
+                                         int64_t lda, const double* B, int64_t ldb, const double* beta, double* C,
+                                         int64_t ldc);
+COSMA_B200_API int cosma_b200_zgemm_host(void* stream, int64_t m, int64_t n, int64_t k, const double* alpha, const double* A,
+                                         int64_t lda, const double* B, int64_t ldb, const double* beta, double* C,
+                                         int64_t ldc);
+/* Number of GEMM kernels launched by the last *_host call on this thread. */
+COSMA_B200_API int cosma_b200_last_launch_count(void);
+/* Frees the device staging workspace cached by the *_host entry points (thread-local). */
+COSMA_B200_API void cosma_b200_release_workspace(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,3 +128,39 @@ void ref_zgemm(int m, int n, int k, const double* alpha, const double* A, int ld
 }  // extern "C"
 
 extern "C" void ref_set_blas_threads(int n) { openblas_set_num_threads(n); }
+
+// ---- timing the reference's own cosma::multiply at P = 1 (bench.py --impl reference / cpu_baseline) ----
+// Mirrors run<T>() of the reference miniapp (miniapp/cosma_miniapp.cpp:35-81): Strategy(m,n,k,1), CosmaMatrix
+// A/B/C in the singleton context, srand48(rank), 10*drand48() fill, alpha = 1, beta = 0, steady_clock around
+// multiply(). Differences: per-repetition times are returned unsorted so warm-up can be dropped, and the
+// matrices are built once.
+#include <cosma/multiply.hpp>
+#include <chrono>
+#include <cstdlib>
+
+extern "C" int ref_multiply_time_d(int m, int n, int k, int reps, double* times_ms, double* checksum) {
+    try {
+        using namespace cosma;
+        Strategy strategy(m, n, k, 1);
+        CosmaMatrix<double> A('A', strategy, 0);
+        CosmaMatrix<double> B('B', strategy, 0);
+        CosmaMatrix<double> C('C', strategy, 0);
+        srand48(0);
+        for (size_t i = 0; i < A.matrix_size(); ++i) A.matrix_pointer()[i] = 10 * drand48();
+        for (size_t i = 0; i < B.matrix_size(); ++i) B.matrix_pointer()[i] = 10 * drand48();
+        for (int r = 0; r < reps; ++r) {
+            auto start = std::chrono::steady_clock::now();
+            multiply(A, B, C, strategy, MPI_COMM_WORLD, 1.0, 0.0);
+            auto end = std::chrono::steady_clock::now();
+            times_ms[r] = std::chrono::duration<double, std::milli>(end - start).count();
+        }
+        if (checksum) {
+            double s = 0;
+            for (size_t i = 0; i < C.matrix_size(); ++i) s += C.matrix_pointer()[i];
+            *checksum = s;
+        }
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
