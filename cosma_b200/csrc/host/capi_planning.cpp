@@ -1,0 +1,89 @@
+// extern "C" access to the host planning layer (Strategy, Mapper): used by the Python mirror, the tests (which pin
+// these against the unmodified reference in oracle/_ref) and by foreign-language hosts.
+#include "../../../include/cosma_b200.h"
+#include <cosma/mapper.hpp>
+#include <cosma/strategy.hpp>
+
+#include <cstring>
+#include <string>
+
+namespace cosma_b200 {
+void set_last_error(const std::string& msg);
+}
+
+extern "C" {
+
+int cosma_b200_strategy(int m, int n, int k, int P, long long mem_limit, const char* prefix, char* out, int out_len,
+                        int* P_out, long long* mem_used) {
+    try {
+        if (mem_limit <= 0) mem_limit = std::numeric_limits<long long>::max();
+        cosma::Strategy st = cosma::parse_strategy(m, n, k, P, prefix ? prefix : "", mem_limit);
+        const std::string s = st.to_string();
+        if (static_cast<int>(s.size()) + 1 > out_len) return COSMA_B200_INVALID_ARG;
+        std::strcpy(out, s.c_str());
+        if (P_out) *P_out = static_cast<int>(st.P);
+        if (mem_used) *mem_used = st.memory_used;
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        cosma_b200::set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+int cosma_b200_mapper_layout(char label, int m, int n, int k, int P, const char* steps, int* counts, int* out, int out_cap,
+                             int* total_blocks) {
+    try {
+        cosma::Strategy st = cosma::parse_strategy(m, n, k, P, steps ? steps : "");
+        cosma::Mapper mapper(label, st, 0);
+        int total = 0;
+        for (int r = 0; r < mapper.P(); ++r) {
+            const auto& blocks = mapper.initial_layout(r);
+            counts[r] = static_cast<int>(blocks.size());
+            for (const auto& b : blocks) {
+                if (4 * (total + 1) > out_cap) return COSMA_B200_INVALID_ARG;
+                out[4 * total + 0] = b.rows.first();
+                out[4 * total + 1] = b.rows.last();
+                out[4 * total + 2] = b.cols.first();
+                out[4 * total + 3] = b.cols.last();
+                ++total;
+            }
+        }
+        if (total_blocks) *total_blocks = total;
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        cosma_b200::set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+int cosma_b200_mapper_local_coordinates(char label, int m, int n, int k, int P, const char* steps, int gi, int gj,
+                                        int64_t* local_idx, int* rank) {
+    try {
+        cosma::Strategy st = cosma::parse_strategy(m, n, k, P, steps ? steps : "");
+        cosma::Mapper mapper(label, st, 0);
+        const auto res = mapper.local_coordinates(gi, gj);
+        *local_idx = res.first;
+        *rank = res.second;
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        cosma_b200::set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+int cosma_b200_mapper_global_coordinates(char label, int m, int n, int k, int P, const char* steps, int64_t local_idx,
+                                         int rank, int* gi, int* gj) {
+    try {
+        cosma::Strategy st = cosma::parse_strategy(m, n, k, P, steps ? steps : "");
+        cosma::Mapper mapper(label, st, 0);
+        const auto res = mapper.global_coordinates(local_idx, rank);
+        *gi = res.first;
+        *gj = res.second;
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        cosma_b200::set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+}  // extern "C"

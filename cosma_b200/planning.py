@@ -1,0 +1,59 @@
+"""Host planning layer through the C ABI: Strategy and Mapper (mirrors cosma::Strategy / cosma::Mapper)."""
+import ctypes
+
+from . import _lib
+
+
+def strategy(m, n, k, P, mem_limit=0, prefix=""):
+    """-> (steps string e.g. 'pm2,pn2,pk2', ranks actually used, elements of memory per rank)"""
+    lib = _lib.load()
+    out = ctypes.create_string_buffer(4096)
+    P_out = ctypes.c_int(0)
+    mem = ctypes.c_longlong(0)
+    st = lib.cosma_b200_strategy(ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(k), ctypes.c_int(P),
+                                 ctypes.c_longlong(mem_limit), prefix.encode(), out, ctypes.c_int(4096),
+                                 ctypes.byref(P_out), ctypes.byref(mem))
+    _lib.check(st, "cosma_b200_strategy")
+    return out.value.decode(), P_out.value, mem.value
+
+
+def mapper_layout(label, m, n, k, P, steps):
+    """-> per rank, list of (row_first, row_last, col_first, col_last) blocks in local-buffer order"""
+    lib = _lib.load()
+    counts = (ctypes.c_int * max(P, 1))()
+    cap = 4 * 65536
+    out = (ctypes.c_int * cap)()
+    total = ctypes.c_int(0)
+    st = lib.cosma_b200_mapper_layout(ctypes.c_char(label.encode()), ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(k),
+                                      ctypes.c_int(P), steps.encode(), counts, out, ctypes.c_int(cap), ctypes.byref(total))
+    _lib.check(st, "cosma_b200_mapper_layout")
+    res, pos = [], 0
+    for r in range(P):
+        blocks = []
+        for _ in range(counts[r]):
+            blocks.append(tuple(out[4 * pos:4 * pos + 4]))
+            pos += 1
+        res.append(blocks)
+    return res
+
+
+def local_coordinates(label, m, n, k, P, steps, gi, gj):
+    lib = _lib.load()
+    li = ctypes.c_int64(0)
+    rk = ctypes.c_int(0)
+    st = lib.cosma_b200_mapper_local_coordinates(ctypes.c_char(label.encode()), ctypes.c_int(m), ctypes.c_int(n),
+                                                 ctypes.c_int(k), ctypes.c_int(P), steps.encode(), ctypes.c_int(gi),
+                                                 ctypes.c_int(gj), ctypes.byref(li), ctypes.byref(rk))
+    _lib.check(st, "cosma_b200_mapper_local_coordinates")
+    return li.value, rk.value
+
+
+def global_coordinates(label, m, n, k, P, steps, local_idx, rank):
+    lib = _lib.load()
+    gi = ctypes.c_int(0)
+    gj = ctypes.c_int(0)
+    st = lib.cosma_b200_mapper_global_coordinates(ctypes.c_char(label.encode()), ctypes.c_int(m), ctypes.c_int(n),
+                                                  ctypes.c_int(k), ctypes.c_int(P), steps.encode(), ctypes.c_int64(local_idx),
+                                                  ctypes.c_int(rank), ctypes.byref(gi), ctypes.byref(gj))
+    _lib.check(st, "cosma_b200_mapper_global_coordinates")
+    return gi.value, gj.value

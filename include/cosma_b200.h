@@ -53,6 +53,23 @@ COSMA_B200_API int cosma_b200_zgemm(void* stream, char transa, char transb, int6
 /* Which kernel the last ?gemm call on this thread used: 0 none, 1 TMA+DMMA persistent, 2 generic. */
 COSMA_B200_API int cosma_b200_last_gemm_path(void);
 
+/* ---- planning layer (host only, no CUDA) --------------------------------------------------------
+ * cosma::Strategy (reference src/cosma/strategy.hpp:16-183) and cosma::Mapper (src/cosma/mapper.hpp:21-126) in
+ * C form. Steps are written as the reference miniapp's -s string: "pm2,sn4,pk2" (p|s)(m|n|k)(divisor).
+ */
+/* Strategy(m,n,k,P[,prefix][,mem_limit in elements, <=0: unlimited]) -> step string in out; *P_out = ranks used
+ * (ranks >= *P_out idle, reference strategy.cpp:139-169); *mem_used = elements per rank. */
+COSMA_B200_API int cosma_b200_strategy(int m, int n, int k, int P, long long mem_limit, const char* prefix, char* out,
+                                       int out_len, int* P_out, long long* mem_used);
+/* Mapper(label in 'A'|'B'|'C').complete_layout(): counts[r] = blocks of rank r; out = [r][block]{row_first,row_last,
+ * col_first,col_last} (inclusive), flattened in local-buffer order. */
+COSMA_B200_API int cosma_b200_mapper_layout(char label, int m, int n, int k, int P, const char* steps, int* counts, int* out,
+                                            int out_cap, int* total_blocks);
+COSMA_B200_API int cosma_b200_mapper_local_coordinates(char label, int m, int n, int k, int P, const char* steps, int gi,
+                                                       int gj, int64_t* local_idx, int* rank);
+COSMA_B200_API int cosma_b200_mapper_global_coordinates(char label, int m, int n, int k, int P, const char* steps,
+                                                        int64_t local_idx, int rank, int* gi, int* gj);
+
 /* ---- local GEMM with HOST operands ('N','N') -------------------------------------------------
  * Same contract as the reference's GPU base case, which receives host pointers and streams tiles
  * through the device (gpu::gemm, libs/Tiled-MM/src/Tiled-MM/tiled_mm.cpp:492-624; copy_c_back = true).

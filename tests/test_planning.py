@@ -1,0 +1,100 @@
+"""Strategy and Mapper (host planning layer, through the C ABI) pinned bit-exactly against
+ (1) the golden vectors of the reference's own unit test tests/mapper.cpp,
+ (2) the unmodified reference built in oracle/_ref (when present), and
+ (3) the committed fixture tests/golden/planning_golden.json generated from it (travels to the GPU box)."""
+import json
+import os
+
+import pytest
+
+from cases import BASELINE_CASES, MEMORY_LIMITED_CASES, REFERENCE_MULTIPLY_CASES, SCALAR_MATMUL_CASE
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "planning_golden.json")
+ALL = REFERENCE_MULTIPLY_CASES + [SCALAR_MATMUL_CASE] + BASELINE_CASES
+
+
+@pytest.fixture(scope="module")
+def planning(lib):
+    from cosma_b200 import planning as p
+    return p
+
+
+def test_golden_strategy_rpa(planning):
+    # reference tests/mapper.cpp:363-387: dims "kkmnkmnkn", types "spppppppp", divisors {16,16,2,2,2,3,2,3,2}
+    s, P, _ = planning.strategy(17408, 17408, 3473408, 4608, 52428800)
+    assert s == "sk16,pk16,pm2,pn2,pk2,pm3,pn2,pk3,pn2"
+    assert P == 4608
+
+
+def test_golden_mapper_tables(planning):
+    # reference tests/mapper.cpp:408-562: (m,n,k,P) = (8,4,2,4), steps pm2,sm2,pn2
+    m, n, k, P, steps = 8, 4, 2, 4, "pm2,sm2,pn2"
+    A = planning.mapper_layout("A", m, n, k, P, steps)
+    B = planning.mapper_layout("B", m, n, k, P, steps)
+    C = planning.mapper_layout("C", m, n, k, P, steps)
+    size = lambda lay: [sum((b[1] - b[0] + 1) * (b[3] - b[2] + 1) for b in blocks) for blocks in lay]
+    assert size(A) == [4, 4, 4, 4] and size(B) == [2, 2, 2, 2] and size(C) == [8, 8, 8, 8]
+    # A: rows split by pm2 (ranks {0,1} | {2,3}), then sm2 gives two buckets per rank, pn2 deals columns of A (k)
+    assert A[0] == [(0, 1, 0, 0), (2, 3, 0, 0)] and A[1] == [(0, 1, 1, 1), (2, 3, 1, 1)]
+    assert A[2] == [(4, 5, 0, 0), (6, 7, 0, 0)] and A[3] == [(4, 5, 1, 1), (6, 7, 1, 1)]
+    # B (k x n = 2 x 4): pm2 is a copy step for B -> columns dealt over the two groups; pn2 splits n
+    assert B[0] == [(0, 1, 0, 0)] and B[2] == [(0, 1, 1, 1)] and B[1] == [(0, 1, 2, 2)] and B[3] == [(0, 1, 3, 3)]
+    assert C[0] == [(0, 1, 0, 1), (2, 3, 0, 1)] and C[3] == [(4, 5, 2, 3), (6, 7, 2, 3)]
+    # global <-> local round trip over the whole matrix
+    for label, rows, cols in (("A", m, k), ("B", k, n), ("C", m, n)):
+        for gi in range(rows):
+            for gj in range(cols):
+                li, rk = planning.local_coordinates(label, m, n, k, P, steps, gi, gj)
+                assert planning.global_coordinates(label, m, n, k, P, steps, li, rk) == (gi, gj)
+
+
+def test_baseline_strategies(planning):
+    # SURVEY.md fact 5 (probe of the reference Strategy)
+    assert planning.strategy(32768, 32768, 32768, 8)[0] == "pm2,pn2,pk2"
+    assert planning.strategy(32768, 32768, 32768, 4)[0] == "pn2,pk2"
+    assert planning.strategy(32768, 32768, 32768, 2)[0] == "pk2"
+    assert planning.strategy(8192, 8192, 1048576, 8)[0] == "pk8"
+    assert planning.strategy(2000, 2000, 2000, 2)[0] == "pk2"
+    assert planning.strategy(16384, 16384, 16384, 1)[0] == ""
+
+
+@pytest.mark.parametrize("case", ALL, ids=lambda c: "%dx%dx%d_P%d_%s" % (c[0], c[1], c[2], c[3], c[4] or "auto"))
+def test_strategy_and_layout_vs_reference(planning, ref, case):
+    m, n, k, P, steps = case
+    try:
+        want = ref.ref_strategy(m, n, k, P, 0, steps)
+    except RuntimeError:
+        with pytest.raises(Exception):
+            planning.strategy(m, n, k, P, 0, steps)
+        return
+    got = planning.strategy(m, n, k, P, 0, steps)
+    assert got == want
+    full = got[0]
+    if P <= 64:
+        for label in "ABC":
+            assert planning.mapper_layout(label, m, n, k, got[1], full) == ref.ref_mapper_layout(label, m, n, k, got[1], full)
+
+
+@pytest.mark.parametrize("case", MEMORY_LIMITED_CASES, ids=lambda c: "%dx%dx%d_P%d_mem%d" % c)
+def test_memory_limited_strategy_vs_reference(planning, ref, case):
+    m, n, k, P, mem = case
+    assert planning.strategy(m, n, k, P, mem) == ref.ref_strategy(m, n, k, P, mem)
+
+
+def test_committed_golden_fixture(planning):
+    """Same comparison against the fixture generated from the reference (tests/golden/make_planning_golden.py)."""
+    with open(GOLDEN) as f:
+        gold = json.load(f)
+    assert len(gold["cases"]) >= 50
+    for c in gold["cases"]:
+        m, n, k, P, steps, mem = c["m"], c["n"], c["k"], c["P"], c["steps_in"], c["mem_limit"]
+        if c["throws"]:
+            with pytest.raises(Exception):
+                planning.strategy(m, n, k, P, mem, steps)
+            continue
+        got = planning.strategy(m, n, k, P, mem, steps)
+        assert [got[0], got[1], got[2]] == [c["steps"], c["P_used"], c["memory_used"]], c
+        for label in "ABC":
+            if label in c["layout"]:
+                lay = planning.mapper_layout(label, m, n, k, c["P_used"], c["steps"])
+                assert [[list(b) for b in blocks] for blocks in lay] == c["layout"][label], (c, label)
