@@ -11,6 +11,23 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
+def _nccl_include():
+    """nccl.h: prefer the header of the NCCL that torch bundles (the one loaded at run time), else the system one."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            p = os.path.join(list(spec.submodule_search_locations)[0], "include")
+            if os.path.exists(os.path.join(p, "nccl.h")):
+                return p
+    except Exception:
+        pass
+    return "/usr/include"
+
+
+NCCL_INC = _nccl_include()
+
+
 def sources():
     out = []
     for root, _, files in os.walk(CSRC):
@@ -42,7 +59,7 @@ def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", os.path.join(HERE, "..", "include"),
-              "-I", CSRC, "-DCOSMA_B200_BUILD"]
+              "-I", CSRC, "-I", NCCL_INC, "-DCOSMA_B200_BUILD"]
     objs = []
     procs = []
     for src in sources():

@@ -1,0 +1,383 @@
+// Executor of a cosma::Schedule on one GPU: the run-time half of cosma::multiply (reference
+// src/cosma/multiply.cpp:243-314). Communication = NCCL over NVLink on per-step ring communicators
+// (the reference's communicator::create_communicators, communicator.cpp:282-308, and gpu::nccl_copy / nccl_reduce,
+// gpu/nccl_utils.cpp:45-280, which stage through host memory around every collective); local compute = the sm_100a
+// DGEMM/ZGEMM kernels. Operands never leave HBM.
+#include "../../include/cosma_b200.h"
+#include "gemm_f64_sm100.h"
+#include "nccl_dyn.h"
+
+#include <cosma/schedule.hpp>
+
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace cosma_b200 {
+void set_last_error(const std::string& msg);
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, size = 1;
+};
+
+struct Plan {
+    cosma::Schedule schedule;
+    char dtype = 'd';
+    int elem_doubles = 1;  // doubles per element: 1 (d) or 2 (z)
+    std::vector<ncclComm_t> ring_comms;  // by Schedule::rings() index
+    int last_launches = 0;
+    std::vector<float> gemm_ms;  // optional per-GEMM timing of the last run
+    std::vector<cudaEvent_t> ev;
+    bool time_gemms = false;
+};
+
+namespace {
+
+// C[i] = beta * C[i] + T[i]  (E1: the reference's host loop, two_sided_communicator.cpp:219-224)
+template <bool CPLX>
+__global__ void axpby_kernel(int64_t n, double br, double bi, double* __restrict__ C, const double* __restrict__ T) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    if (!CPLX) {
+        const int64_t n2 = n / 2;
+        const bool vec = ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(T)) & 15) == 0;
+        if (vec) {
+            double2* c2 = reinterpret_cast<double2*>(C);
+            const double2* t2 = reinterpret_cast<const double2*>(T);
+            for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n2; i += stride) {
+                double2 c = c2[i];
+                const double2 t = t2[i];
+                c.x = br * c.x + t.x;
+                c.y = br * c.y + t.y;
+                c2[i] = c;
+            }
+            if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) C[n - 1] = br * C[n - 1] + T[n - 1];
+        } else {
+            for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += stride) C[i] = br * C[i] + T[i];
+        }
+    } else {
+        for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += stride) {
+            const double cr = C[2 * i], ci = C[2 * i + 1];
+            C[2 * i] = br * cr - bi * ci + T[2 * i];
+            C[2 * i + 1] = br * ci + bi * cr + T[2 * i + 1];
+        }
+    }
+}
+
+#define NCCL_TRY(call)                                                                     \
+    do {                                                                                   \
+        ncclResult_t r_ = (call);                                                          \
+        if (r_ != ncclSuccess) {                                                           \
+            set_last_error(std::string(#call) + ": " + nccl()->GetErrorString(r_));        \
+            return COSMA_B200_NCCL_ERROR;                                                  \
+        }                                                                                  \
+    } while (0)
+#define CUDA_TRY(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_));            \
+            return COSMA_B200_CUDA_ERROR;                                                  \
+        }                                                                                  \
+    } while (0)
+
+int run_allgather(const Plan& plan, const cosma::ScheduleOp& op, double* arena, cudaStream_t stream) {
+    const NcclApi* N = nccl();
+    const int E = plan.elem_doubles;
+    ncclComm_t comm = plan.ring_comms[op.ring_index];
+    const int div = static_cast<int>(op.ring.size());
+    const size_t nb = op.piece[0].size();
+    const double* src = arena + op.src_off * E;
+    double* dst = arena + op.dst_off * E;
+    if (op.regular) {
+        NCCL_TRY(N->AllGather(src, dst, static_cast<size_t>(op.piece[0][0]) * E, ncclDouble, comm, stream));
+        return COSMA_B200_OK;
+    }
+    // exact placement: bucket-major destination, member-major inside a bucket
+    std::vector<int64_t> src_off(div, 0);
+    int64_t dst_off = 0;
+    NCCL_TRY(N->GroupStart());
+    for (size_t b = 0; b < nb; ++b) {
+        for (int g = 0; g < div; ++g) {
+            const int64_t cnt = op.piece[g][b];
+            if (cnt > 0) {
+                if (g == op.my_pos) {
+                    CUDA_TRY(cudaMemcpyAsync(dst + dst_off * E, src + src_off[g] * E, cnt * E * sizeof(double),
+                                             cudaMemcpyDeviceToDevice, stream));
+                } else {
+                    NCCL_TRY(N->Recv(dst + dst_off * E, static_cast<size_t>(cnt) * E, ncclDouble, g, comm, stream));
+                }
+            }
+            src_off[g] += cnt;
+            dst_off += cnt;
+        }
+        // my piece of this bucket goes to every other member
+        const int64_t mine = op.piece[op.my_pos][b];
+        if (mine > 0)
+            for (int g = 0; g < div; ++g)
+                if (g != op.my_pos)
+                    NCCL_TRY(N->Send(src + (src_off[op.my_pos] - mine) * E, static_cast<size_t>(mine) * E, ncclDouble, g, comm, stream));
+    }
+    NCCL_TRY(N->GroupEnd());
+    return COSMA_B200_OK;
+}
+
+int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, double* arena, const double* beta_user, cudaStream_t stream) {
+    const NcclApi* N = nccl();
+    const int E = plan.elem_doubles;
+    ncclComm_t comm = plan.ring_comms[op.ring_index];
+    const int div = static_cast<int>(op.ring.size());
+    const size_t nb = op.piece[0].size();
+    double br = 0.0, bi = 0.0;
+    if (op.beta == cosma::BetaMode::ONE) br = 1.0;
+    else if (op.beta == cosma::BetaMode::USER) { br = beta_user[0]; bi = E == 2 ? beta_user[1] : 0.0; }
+    const bool beta_zero = br == 0.0 && bi == 0.0;
+    const double* src = arena + op.src_off * E;
+    double* dst = arena + op.dst_off * E;
+    double* recv = beta_zero ? dst : arena + op.tmp_off * E;
+    int64_t mine_total = 0;
+    for (auto v : op.piece[op.my_pos]) mine_total += v;
+    if (op.regular) {
+        NCCL_TRY(N->ReduceScatter(src, recv, static_cast<size_t>(op.piece[0][0]) * E, ncclDouble, ncclSum, comm, stream));
+    } else {
+        // reduce-scatter-v with exact counts: one rooted reduction per (bucket, member), fused in one NCCL group
+        int64_t off = 0, roff = 0;
+        NCCL_TRY(N->GroupStart());
+        for (size_t b = 0; b < nb; ++b)
+            for (int g = 0; g < div; ++g) {
+                const int64_t cnt = op.piece[g][b];
+                if (cnt > 0)
+                    NCCL_TRY(N->Reduce(src + off * E, g == op.my_pos ? recv + roff * E : nullptr, static_cast<size_t>(cnt) * E,
+                                       ncclDouble, ncclSum, g, comm, stream));
+                if (g == op.my_pos) roff += cnt;
+                off += cnt;
+            }
+        NCCL_TRY(N->GroupEnd());
+    }
+    if (!beta_zero && mine_total > 0) {
+        const int threads = 256;
+        const int64_t work = E == 2 ? mine_total : (mine_total + 1) / 2;
+        int blocks = static_cast<int>(std::min<int64_t>((work + threads - 1) / threads, 148 * 8));
+        if (blocks < 1) blocks = 1;
+        if (E == 1) axpby_kernel<false><<<blocks, threads, 0, stream>>>(mine_total, br, bi, dst, recv);
+        else axpby_kernel<true><<<blocks, threads, 0, stream>>>(mine_total, br, bi, dst, recv);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return COSMA_B200_OK;
+}
+
+}  // namespace
+
+int plan_run(Plan& plan, const double* alpha, const double* beta, double* A, double* B, double* C, cudaStream_t stream) {
+    const int E = plan.elem_doubles;
+    double* arenas[3] = {A, B, C};
+    plan.last_launches = 0;
+    size_t n_gemm = 0;
+    for (const auto& op : plan.schedule.ops()) n_gemm += op.kind == cosma::OpKind::GEMM;
+    if (plan.time_gemms) {
+        while (plan.ev.size() < 2 * n_gemm) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            plan.ev.push_back(e);
+        }
+    }
+    size_t gi = 0;
+    for (const auto& op : plan.schedule.ops()) {
+        int st = COSMA_B200_OK;
+        switch (op.kind) {
+            case cosma::OpKind::GEMM: {
+                double b[2] = {0.0, 0.0};
+                if (op.beta == cosma::BetaMode::ONE) b[0] = 1.0;
+                else if (op.beta == cosma::BetaMode::USER) { b[0] = beta[0]; b[1] = E == 2 ? beta[1] : 0.0; }
+                int path = 0;
+                if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * gi], stream));
+                if (E == 1)
+                    st = dgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha[0], A + op.a_off, std::max(op.m, 1), B + op.b_off,
+                                     std::max(op.k, 1), b[0], C + op.c_off, std::max(op.m, 1), &path);
+                else
+                    st = zgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha, A + 2 * op.a_off, std::max(op.m, 1),
+                                     B + 2 * op.b_off, std::max(op.k, 1), b, C + 2 * op.c_off, std::max(op.m, 1), &path);
+                if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * gi + 1], stream));
+                ++gi;
+                if (path) ++plan.last_launches;
+                break;
+            }
+            case cosma::OpKind::ALLGATHER:
+                st = run_allgather(plan, op, arenas[op.matrix], stream);
+                break;
+            case cosma::OpKind::REDUCE:
+                st = run_reduce(plan, op, arenas[op.matrix], beta, stream);
+                break;
+        }
+        if (st != COSMA_B200_OK) return st;
+    }
+    return COSMA_B200_OK;
+}
+
+}  // namespace cosma_b200
+
+using cosma_b200::Comm;
+using cosma_b200::Plan;
+using cosma_b200::nccl;
+using cosma_b200::set_last_error;
+
+extern "C" {
+
+int cosma_b200_nccl_unique_id(uint8_t* out128) {
+    const auto* N = nccl();
+    if (!N) return COSMA_B200_NCCL_ERROR;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (N->GetUniqueId(&id) != ncclSuccess) return COSMA_B200_NCCL_ERROR;
+    std::memcpy(out128, &id, 128);
+    return COSMA_B200_OK;
+}
+
+int cosma_b200_comm_create(int rank, int nranks, const uint8_t* id128, void** comm_out) {
+    const auto* N = nccl();
+    if (!N) return COSMA_B200_NCCL_ERROR;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    auto c = std::make_unique<Comm>();
+    c->rank = rank;
+    c->size = nranks;
+    ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        set_last_error(std::string("ncclCommInitRank: ") + N->GetErrorString(r));
+        return COSMA_B200_NCCL_ERROR;
+    }
+    *comm_out = c.release();
+    return COSMA_B200_OK;
+}
+
+int cosma_b200_comm_destroy(void* comm) {
+    Comm* c = static_cast<Comm*>(comm);
+    if (!c) return COSMA_B200_OK;
+    if (c->comm && nccl()) nccl()->CommDestroy(c->comm);
+    delete c;
+    return COSMA_B200_OK;
+}
+
+int cosma_b200_plan_create(void* comm, int rank, int nranks, int m, int n, int k, const char* steps, char dtype,
+                           void** plan_out) {
+    try {
+        if (dtype != 'd' && dtype != 'z') {
+            set_last_error("plan dtype must be 'd' or 'z'");
+            return COSMA_B200_NOT_SUPPORTED;
+        }
+        Comm* c = static_cast<Comm*>(comm);
+        if (c) { rank = c->rank; nranks = c->size; }
+        cosma::Strategy strategy = cosma::parse_strategy(m, n, k, nranks, steps ? steps : "");
+        auto plan = std::make_unique<Plan>();
+        plan->schedule = cosma::Schedule(strategy, rank);
+        plan->dtype = dtype;
+        plan->elem_doubles = dtype == 'z' ? 2 : 1;
+        if (c && nranks > 1) {
+            const auto* N = nccl();
+            // one communicator split per parallel step, called by EVERY rank of the parent communicator in step
+            // order (idle ranks and ranks outside a ring pass NCCL_SPLIT_NOCOLOR)
+            std::vector<int> par_steps;
+            for (size_t s = 0; s < strategy.n_steps(); ++s)
+                if (strategy.parallel_step(s)) par_steps.push_back(static_cast<int>(s));
+            const auto& rings = plan->schedule.rings();
+            plan->ring_comms.assign(rings.size(), nullptr);
+            for (int s : par_steps) {
+                int color = NCCL_SPLIT_NOCOLOR, key = 0, idx = -1;
+                for (size_t i = 0; i < rings.size(); ++i)
+                    if (rings[i].step == s) { color = rings[i].color; key = rings[i].my_pos; idx = static_cast<int>(i); }
+                ncclComm_t sub = nullptr;
+                ncclResult_t r = N->CommSplit(c->comm, color, key, &sub, nullptr);
+                if (r != ncclSuccess) {
+                    set_last_error(std::string("ncclCommSplit: ") + N->GetErrorString(r));
+                    return COSMA_B200_NCCL_ERROR;
+                }
+                if (idx >= 0) plan->ring_comms[idx] = sub;
+            }
+        }
+        *plan_out = plan.release();
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+int cosma_b200_plan_destroy(void* plan) {
+    Plan* p = static_cast<Plan*>(plan);
+    if (!p) return COSMA_B200_OK;
+    for (auto c : p->ring_comms)
+        if (c && nccl()) nccl()->CommDestroy(c);
+    for (auto e : p->ev) cudaEventDestroy(e);
+    delete p;
+    return COSMA_B200_OK;
+}
+
+int64_t cosma_b200_plan_arena_elements(void* plan, int matrix) {
+    return static_cast<Plan*>(plan)->schedule.arena_elements(matrix);
+}
+int64_t cosma_b200_plan_initial_elements(void* plan, int matrix) {
+    return static_cast<Plan*>(plan)->schedule.initial_elements(matrix);
+}
+int cosma_b200_plan_strategy(void* plan, char* out, int out_len, int* P_used) {
+    const auto& st = static_cast<Plan*>(plan)->schedule.strategy();
+    const std::string s = st.to_string();
+    if (static_cast<int>(s.size()) + 1 > out_len) return COSMA_B200_INVALID_ARG;
+    std::strcpy(out, s.c_str());
+    if (P_used) *P_used = static_cast<int>(st.P);
+    return COSMA_B200_OK;
+}
+double cosma_b200_plan_gemm_flops(void* plan) {
+    Plan* p = static_cast<Plan*>(plan);
+    return p->schedule.total_gemm_flops() * (p->elem_doubles == 2 ? 4.0 : 1.0);
+}
+int cosma_b200_plan_export(void* plan, int64_t* buf, int64_t cap, int64_t* len) {
+    const auto v = static_cast<Plan*>(plan)->schedule.serialize();
+    *len = static_cast<int64_t>(v.size());
+    if (buf && cap >= *len) std::memcpy(buf, v.data(), v.size() * sizeof(int64_t));
+    return COSMA_B200_OK;
+}
+int cosma_b200_plan_local_blocks(void* plan, int matrix, int rank, int* out, int cap, int* n_blocks) {
+    const auto& blocks = static_cast<Plan*>(plan)->schedule.mapper(matrix).initial_layout(rank);
+    *n_blocks = static_cast<int>(blocks.size());
+    if (out && cap >= 4 * *n_blocks)
+        for (int i = 0; i < *n_blocks; ++i) {
+            out[4 * i] = blocks[i].rows.first(); out[4 * i + 1] = blocks[i].rows.last();
+            out[4 * i + 2] = blocks[i].cols.first(); out[4 * i + 3] = blocks[i].cols.last();
+        }
+    return COSMA_B200_OK;
+}
+
+int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, void* A, void* B, void* C, void* stream) {
+    Plan* p = static_cast<Plan*>(plan);
+    if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
+    if (p->schedule.idle()) return COSMA_B200_OK;
+    bool needs_comm = false;
+    for (const auto& op : p->schedule.ops()) needs_comm |= op.kind != cosma::OpKind::GEMM;
+    if (needs_comm && p->ring_comms.empty()) {
+        set_last_error("plan was created without a communicator (plan-only); cannot execute collectives");
+        return COSMA_B200_INVALID_ARG;
+    }
+    return cosma_b200::plan_run(*p, alpha, beta, static_cast<double*>(A), static_cast<double*>(B), static_cast<double*>(C),
+                                static_cast<cudaStream_t>(stream));
+}
+
+int cosma_b200_plan_last_launches(void* plan) { return static_cast<Plan*>(plan)->last_launches; }
+
+int cosma_b200_plan_time_gemms(void* plan, int enable) {
+    static_cast<Plan*>(plan)->time_gemms = enable != 0;
+    return COSMA_B200_OK;
+}
+/* after a synchronised run with timing enabled: per-GEMM device milliseconds */
+int cosma_b200_plan_gemm_times(void* plan, float* out, int cap, int* n) {
+    Plan* p = static_cast<Plan*>(plan);
+    int cnt = 0;
+    for (const auto& op : p->schedule.ops()) cnt += op.kind == cosma::OpKind::GEMM;
+    *n = cnt;
+    if (!p->time_gemms || static_cast<int>(p->ev.size()) < 2 * cnt) return COSMA_B200_INVALID_ARG;
+    for (int i = 0; i < cnt && i < cap; ++i)
+        if (cudaEventElapsedTime(&out[i], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+    return COSMA_B200_OK;
+}
+
+}  // extern "C"

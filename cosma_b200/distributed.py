@@ -1,0 +1,204 @@
+"""Host-side mirror of cosma::multiply for one-process-per-GPU jobs (torch.distributed for rendezvous only).
+
+  comm = init_comm()                              # ncclUniqueId broadcast over torch.distributed -> ncclCommInitRank
+  plan = MultiplyPlan(comm, m, n, k, steps="", dtype="d")
+  plan.A.local[...] = ...                         # the rank's local matrix in the reference's layout
+  plan.multiply(alpha, beta)                      # C = alpha*A*B + beta*C, asynchronous on the current stream
+
+Mirrors: CosmaMatrix<T> A('A', strategy, rank) / matrix_pointer() / matrix_size() and
+multiply(A, B, C, strategy, comm, alpha, beta) (reference src/cosma/matrix.hpp:26-213, multiply.hpp:47-54)."""
+import ctypes
+
+from . import _lib
+
+_MAT = {"A": 0, "B": 1, "C": 2}
+
+
+def _declare(lib):
+    if getattr(lib, "_dist_declared", False):
+        return
+    vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.cosma_b200_comm_create.argtypes = [ci, ci, ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.cosma_b200_comm_destroy.argtypes = [vp]
+    lib.cosma_b200_plan_create.argtypes = [vp, ci, ci, ci, ci, ci, ctypes.c_char_p, ctypes.c_char, ctypes.POINTER(vp)]
+    lib.cosma_b200_plan_destroy.argtypes = [vp]
+    lib.cosma_b200_plan_arena_elements.argtypes = [vp, ci]
+    lib.cosma_b200_plan_arena_elements.restype = i64
+    lib.cosma_b200_plan_initial_elements.argtypes = [vp, ci]
+    lib.cosma_b200_plan_initial_elements.restype = i64
+    lib.cosma_b200_plan_strategy.argtypes = [vp, ctypes.c_char_p, ci, ctypes.POINTER(ci)]
+    lib.cosma_b200_plan_gemm_flops.argtypes = [vp]
+    lib.cosma_b200_plan_gemm_flops.restype = ctypes.c_double
+    lib.cosma_b200_plan_export.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(i64)]
+    lib.cosma_b200_plan_local_blocks.argtypes = [vp, ci, ci, ctypes.POINTER(ci), ci, ctypes.POINTER(ci)]
+    lib.cosma_b200_multiply.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp, vp, vp, vp]
+    lib.cosma_b200_plan_last_launches.argtypes = [vp]
+    lib.cosma_b200_plan_time_gemms.argtypes = [vp, ci]
+    lib.cosma_b200_plan_gemm_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci, ctypes.POINTER(ci)]
+    lib._dist_declared = True
+
+
+class Comm:
+    """NCCL communicator of the whole job (the reference's MPI_Comm argument)."""
+
+    def __init__(self, handle, rank, size):
+        self.handle, self.rank, self.size = handle, rank, size
+
+    def destroy(self):
+        if self.handle:
+            _lib.load().cosma_b200_comm_destroy(self.handle)
+            self.handle = None
+
+
+def init_comm(device=None):
+    """Collective over torch.distributed's default group. Single-process jobs get a trivial communicator."""
+    import torch
+    import torch.distributed as dist
+    lib = _lib.load()
+    _declare(lib)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return Comm(None, 0, 1)
+    rank, size = dist.get_rank(), dist.get_world_size()
+    uid = (ctypes.c_uint8 * 128)()
+    if rank == 0:
+        _lib.check(lib.cosma_b200_nccl_unique_id(uid), "cosma_b200_nccl_unique_id")
+    on_gpu = dist.get_backend() == "nccl"
+    t = torch.tensor(list(uid), dtype=torch.uint8, device=(device or torch.device("cuda", torch.cuda.current_device())) if on_gpu else "cpu")
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    handle = ctypes.c_void_p()
+    _lib.check(lib.cosma_b200_comm_create(rank, size, raw, ctypes.byref(handle)), "cosma_b200_comm_create")
+    return Comm(handle, rank, size)
+
+
+def parse_plan(flat):
+    """Decodes cosma_b200_plan_export (see csrc/host/schedule.cpp) into a list of dicts."""
+    ops, i = [], 0
+    while i < len(flat):
+        kind = flat[i]; i += 1
+        if kind == 0:
+            a, b, c, m, n, k, beta = flat[i:i + 7]; i += 7
+            ops.append({"kind": "gemm", "a_off": a, "b_off": b, "c_off": c, "m": m, "n": n, "k": k, "beta": beta})
+            continue
+        matrix, step, ring_index, my_pos, src, dst = flat[i:i + 6]; i += 6
+        op = {"kind": "allgather" if kind == 1 else "reduce", "matrix": matrix, "step": step, "ring_index": ring_index,
+              "my_pos": my_pos, "src_off": src, "dst_off": dst}
+        if kind == 2:
+            op["tmp_off"], op["beta"] = flat[i], flat[i + 1]; i += 2
+        div, nb, regular = flat[i:i + 3]; i += 3
+        op["regular"] = bool(regular)
+        op["ring"] = list(flat[i:i + div]); i += div
+        op["piece"] = [list(flat[i + g * nb:i + (g + 1) * nb]) for g in range(div)]; i += div * nb
+        ops.append(op)
+    return ops
+
+
+class LocalMatrix:
+    """One matrix of a plan on this rank: device arena + the view of the rank's local data (CosmaMatrix analogue)."""
+
+    def __init__(self, label, arena, initial):
+        self.label, self.arena, self.initial = label, arena, initial
+
+    @property
+    def local(self):  # matrix_pointer() / matrix_size()
+        return self.arena[:self.initial]
+
+
+class MultiplyPlan:
+    def __init__(self, comm, m, n, k, steps="", dtype="d", rank=None, nranks=None, device=None, allocate=True):
+        lib = _lib.load()
+        _declare(lib)
+        self.lib, self.comm, self.m, self.n, self.k, self.dtype = lib, comm, m, n, k, dtype
+        self.rank = comm.rank if comm is not None and rank is None else (rank or 0)
+        self.nranks = comm.size if comm is not None and nranks is None else (nranks or 1)
+        h = ctypes.c_void_p()
+        ch = comm.handle if comm is not None else None
+        _lib.check(lib.cosma_b200_plan_create(ch, self.rank, self.nranks, m, n, k, steps.encode(), ctypes.c_char(dtype.encode()),
+                                              ctypes.byref(h)), "cosma_b200_plan_create")
+        self.handle = h
+        buf = ctypes.create_string_buffer(4096)
+        P = ctypes.c_int(0)
+        _lib.check(lib.cosma_b200_plan_strategy(h, buf, 4096, ctypes.byref(P)), "cosma_b200_plan_strategy")
+        self.strategy, self.P_used = buf.value.decode(), P.value
+        self.idle = self.rank >= self.P_used
+        self.arena_elements = [lib.cosma_b200_plan_arena_elements(h, x) for x in range(3)]
+        self.initial_elements = [lib.cosma_b200_plan_initial_elements(h, x) for x in range(3)]
+        self.gemm_flops = lib.cosma_b200_plan_gemm_flops(h)
+        self.A = self.B = self.C = None
+        if allocate:
+            import torch
+            tdt = {"d": torch.float64, "z": torch.complex128}[dtype]
+            dev = device or torch.device("cuda", torch.cuda.current_device())
+            mats = []
+            for x, label in enumerate("ABC"):
+                arena = torch.zeros(max(self.arena_elements[x], 1), dtype=tdt, device=dev)
+                mats.append(LocalMatrix(label, arena, self.initial_elements[x]))
+            self.A, self.B, self.C = mats
+
+    def ops(self):
+        n = ctypes.c_int64(0)
+        self.lib.cosma_b200_plan_export(self.handle, None, 0, ctypes.byref(n))
+        buf = (ctypes.c_int64 * max(n.value, 1))()
+        self.lib.cosma_b200_plan_export(self.handle, buf, n.value, ctypes.byref(n))
+        return parse_plan(list(buf[:n.value]))
+
+    def local_blocks(self, label, rank=None):
+        """Blocks (row_first,row_last,col_first,col_last) of `rank` (default: this rank) in local-buffer order."""
+        rank = self.rank if rank is None else rank
+        if rank >= self.P_used:
+            return []
+        n = ctypes.c_int(0)
+        self.lib.cosma_b200_plan_local_blocks(self.handle, _MAT[label], rank, None, 0, ctypes.byref(n))
+        out = (ctypes.c_int * max(4 * n.value, 1))()
+        self.lib.cosma_b200_plan_local_blocks(self.handle, _MAT[label], rank, out, 4 * n.value, ctypes.byref(n))
+        return [tuple(out[4 * i:4 * i + 4]) for i in range(n.value)]
+
+    def multiply(self, alpha=1.0, beta=0.0, stream=None):
+        import torch
+        if self.dtype == "d":
+            al = (ctypes.c_double * 1)(float(alpha)); be = (ctypes.c_double * 1)(float(beta))
+        else:
+            al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+            be = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
+        s = stream if stream is not None else torch.cuda.current_stream()
+        st = self.lib.cosma_b200_multiply(self.handle, al, be, ctypes.c_void_p(self.A.arena.data_ptr()),
+                                          ctypes.c_void_p(self.B.arena.data_ptr()), ctypes.c_void_p(self.C.arena.data_ptr()),
+                                          ctypes.c_void_p(s.cuda_stream))
+        _lib.check(st, "cosma_b200_multiply")
+        return self.lib.cosma_b200_plan_last_launches(self.handle)
+
+    def time_gemms(self, enable=True):
+        self.lib.cosma_b200_plan_time_gemms(self.handle, 1 if enable else 0)
+
+    def gemm_times_ms(self):
+        n = ctypes.c_int(0)
+        out = (ctypes.c_float * 4096)()
+        st = self.lib.cosma_b200_plan_gemm_times(self.handle, out, 4096, ctypes.byref(n))
+        _lib.check(st, "cosma_b200_plan_gemm_times")
+        return list(out[:n.value])
+
+    def destroy(self):
+        if self.handle:
+            self.lib.cosma_b200_plan_destroy(self.handle)
+            self.handle = None
+
+
+def fill_local_from_global(plan, label, local, full):
+    """Scatter: copies this rank's blocks of the (rows x cols, torch or numpy, indexable [i, j]) global matrix into
+    the local buffer, block after block, column-major inside a block -- the reference's layout."""
+    pos = 0
+    for (r0, r1, c0, c1) in plan.local_blocks(label):
+        blk = full[r0:r1 + 1, c0:c1 + 1]
+        cnt = (r1 - r0 + 1) * (c1 - c0 + 1)
+        local[pos:pos + cnt] = blk.T.reshape(-1)
+        pos += cnt
+    return pos
+
+
+def gather_local_to_global(plan, label, local, full, rank=None):
+    pos = 0
+    for (r0, r1, c0, c1) in plan.local_blocks(label, rank):
+        nr, nc = r1 - r0 + 1, c1 - c0 + 1
+        full[r0:r1 + 1, c0:c1 + 1] = local[pos:pos + nr * nc].reshape(nc, nr).T
+        pos += nr * nc
+    return pos

@@ -70,6 +70,41 @@ COSMA_B200_API int cosma_b200_mapper_local_coordinates(char label, int m, int n,
 COSMA_B200_API int cosma_b200_mapper_global_coordinates(char label, int m, int n, int k, int P, const char* steps,
                                                         int64_t local_idx, int rank, int* gi, int* gj);
 
+/* ---- distributed multiply ------------------------------------------------------------------------
+ * cosma::multiply(A, B, C, strategy, comm, alpha, beta) (reference src/cosma/multiply.hpp:47-54, multiply.cpp:222-314)
+ * split into its plan-time and run-time halves. One process per GPU; the caller selects the device first.
+ *
+ * Communicator: the reference turns an MPI_Comm into NCCL communicators by broadcasting an ncclUniqueId over MPI
+ * (src/cosma/gpu/nccl_utils.cpp:21-42). Here the host does that broadcast with whatever it has (MPI_Bcast,
+ * torch.distributed, a file) and hands the 128 bytes in.
+ */
+COSMA_B200_API int cosma_b200_nccl_unique_id(uint8_t* out128);                 /* call on one rank, broadcast */
+COSMA_B200_API int cosma_b200_comm_create(int rank, int nranks, const uint8_t* id128, void** comm_out);
+COSMA_B200_API int cosma_b200_comm_destroy(void* comm);
+/* Plan = Strategy + Mapper x3 + compiled schedule + one ring communicator per parallel step (created collectively:
+ * every rank of `comm` must call this with the same m, n, k, steps). comm == NULL builds the plan only (any rank of
+ * any nranks; no execution) -- used by tests and tools. steps: "" = automatic (Strategy(m,n,k,P)), else e.g.
+ * "pm2,pn2,pk2". dtype: 'd' (double) | 'z' (complex double). */
+COSMA_B200_API int cosma_b200_plan_create(void* comm, int rank, int nranks, int m, int n, int k, const char* steps, char dtype,
+                                          void** plan_out);
+COSMA_B200_API int cosma_b200_plan_destroy(void* plan);
+/* Arena sizes in elements. matrix: 0 = A, 1 = B, 2 = C. The first initial_elements of an arena are the rank's local
+ * matrix in the reference's layout (CosmaMatrix::matrix_pointer(), matrix_size(); src/cosma/matrix.hpp:26-213); the
+ * rest is communication workspace. */
+COSMA_B200_API int64_t cosma_b200_plan_arena_elements(void* plan, int matrix);
+COSMA_B200_API int64_t cosma_b200_plan_initial_elements(void* plan, int matrix);
+COSMA_B200_API int cosma_b200_plan_strategy(void* plan, char* out, int out_len, int* P_used);
+COSMA_B200_API double cosma_b200_plan_gemm_flops(void* plan);                  /* real flops of this rank's local GEMMs */
+COSMA_B200_API int cosma_b200_plan_export(void* plan, int64_t* buf, int64_t cap, int64_t* len); /* see schedule.cpp */
+COSMA_B200_API int cosma_b200_plan_local_blocks(void* plan, int matrix, int rank, int* out, int cap, int* n_blocks);
+/* C = alpha*A*B + beta*C on the plan's layout. A, B, C: DEVICE arenas of at least plan_arena_elements each; alpha,
+ * beta: host pointers (1 double, or 2 for 'z'). Asynchronous on `stream`. Idle ranks return immediately. */
+COSMA_B200_API int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, void* A, void* B, void* C,
+                                       void* stream);
+COSMA_B200_API int cosma_b200_plan_last_launches(void* plan);                  /* GEMM kernels launched by the last run */
+COSMA_B200_API int cosma_b200_plan_time_gemms(void* plan, int enable);         /* record CUDA events around each GEMM */
+COSMA_B200_API int cosma_b200_plan_gemm_times(void* plan, float* out_ms, int cap, int* n);
+
 /* ---- local GEMM with HOST operands ('N','N') -------------------------------------------------
  * Same contract as the reference's GPU base case, which receives host pointers and streams tiles
  * through the device (gpu::gemm, libs/Tiled-MM/src/Tiled-MM/tiled_mm.cpp:492-624; copy_c_back = true).

@@ -1,0 +1,61 @@
+"""The compiled multiply schedule (cosma::Schedule via the C ABI) on CPU: every rank's op list is interpreted in
+lockstep with numpy (tests/schedule_sim.py) and the gathered C must equal the dense product EXACTLY on
+integer-valued inputs -- for the reference's 40 distributed test cases (tests/multiply.cpp:142-321, alpha=beta=1 as in
+utils/cosma_utils.hpp:43-44), its mixed sequential/parallel all-types case (tests/scalar_matmul.cpp) and small
+versions of the BASELINE strategies."""
+import numpy as np
+import pytest
+
+from cases import REFERENCE_MULTIPLY_CASES, SCALAR_MATMUL_CASE
+from schedule_sim import simulate
+
+IDS = lambda c: "%dx%dx%d_P%d_%s" % (c[0], c[1], c[2], c[3], c[4] or "auto")
+
+
+@pytest.mark.parametrize("case", REFERENCE_MULTIPLY_CASES, ids=IDS)
+def test_reference_multiply_cases(lib, case):
+    m, n, k, P, steps = case
+    got, want, _ = simulate(m, n, k, P, steps, alpha=1.0, beta=1.0)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", ["d", "z"])
+@pytest.mark.parametrize("beta", [0.0, 1.0, 2.0])
+def test_scalar_matmul_strategy(lib, dtype, beta):
+    m, n, k, P, steps = SCALAR_MATMUL_CASE
+    got, want, _ = simulate(m, n, k, P, steps, alpha=1.0, beta=beta, dtype=dtype)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("case", [
+    (512, 512, 512, 8, "pm2,pn2,pk2"), (512, 512, 512, 4, "pn2,pk2"), (512, 512, 512, 2, "pk2"), (256, 256, 4096, 8, "pk8"),
+    (384, 256, 640, 8, "sk2,sm2,pk2,pm4"), (300, 301, 302, 6, "pk3,pm2"), (97, 101, 103, 4, "pk2,pk2"),
+    (64, 64, 640, 4, "pk2,sk5,pk2"), (250, 130, 70, 8, "pn2,sm3,pm2,sk2,pk2"),
+], ids=IDS)
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_baseline_shaped_strategies(lib, case, beta):
+    m, n, k, P, steps = case
+    got, want, _ = simulate(m, n, k, P, steps, alpha=2.0, beta=beta)
+    assert np.array_equal(got, want)
+
+
+def test_idle_ranks_when_problem_is_small(lib):
+    # automatic strategy drops ranks when a local dimension would fall under COSMA_MIN_LOCAL_DIMENSION
+    got, want, P_used = simulate(300, 300, 300, 8, "", alpha=1.0, beta=0.0)
+    assert P_used < 8
+    assert np.array_equal(got, want)
+
+
+def test_arena_is_bounded(lib):
+    """Stack allocation of communication buffers: the arena never exceeds initial + sum over nesting depth."""
+    from cosma_b200.distributed import MultiplyPlan
+    pl = MultiplyPlan(None, 32768, 32768, 32768, "", "d", rank=3, nranks=8, allocate=False)
+    assert pl.strategy == "pm2,pn2,pk2"
+    local = 16384 * 8192
+    assert pl.initial_elements == [local, local, local]
+    # A expanded once (pn2), B once (pm2): arena = local + 2*local; C expanded once (pk2) plus the staging slice the
+    # reduce-scatter lands in when beta != 0: local + 2*local + local
+    assert pl.arena_elements == [3 * local, 3 * local, 4 * local]
+    kinds = [(op["kind"], op.get("matrix"), op.get("ring")) for op in pl.ops()]
+    assert kinds == [("allgather", 1, [3, 7]), ("allgather", 0, [1, 3]), ("gemm", None, None), ("reduce", 2, [2, 3])]
+    pl.destroy()
