@@ -31,6 +31,8 @@ struct Plan {
     std::vector<float> gemm_ms;  // optional per-GEMM timing of the last run
     std::vector<cudaEvent_t> ev;
     bool time_gemms = false;
+    // library-owned device arenas for the host-pointer entry point (allocated on first use)
+    double* owned[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -309,6 +311,8 @@ int cosma_b200_plan_destroy(void* plan) {
     for (auto c : p->ring_comms)
         if (c && nccl()) nccl()->CommDestroy(c);
     for (auto e : p->ev) cudaEventDestroy(e);
+    for (auto& a : p->owned)
+        if (a) cudaFree(a);
     delete p;
     return COSMA_B200_OK;
 }
@@ -360,6 +364,40 @@ int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, voi
     }
     return cosma_b200::plan_run(*p, alpha, beta, static_cast<double*>(A), static_cast<double*>(B), static_cast<double*>(C),
                                 static_cast<cudaStream_t>(stream));
+}
+
+/* Host-pointer variant: local A, B (and C when beta != 0) are uploaded from (pinned) host memory into arenas owned by
+ * the plan, the schedule runs from HBM, and local C is downloaded; everything is ordered on `stream`. This is the
+ * calling convention of the reference, whose CosmaMatrix buffers live in host memory even in GPU/NCCL builds
+ * (src/cosma/local_multiply.cpp:341-363, gpu/nccl_utils.cpp:98,124-135). */
+int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta, const void* A, const void* B, void* C,
+                             void* stream) {
+    Plan* p = static_cast<Plan*>(plan);
+    if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
+    if (p->schedule.idle()) return COSMA_B200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t es = sizeof(double) * p->elem_doubles;
+    for (int x = 0; x < 3; ++x)
+        if (!p->owned[x]) {
+            const size_t bytes = std::max<size_t>(p->schedule.arena_elements(x), 1) * es;
+            if (cudaMalloc(reinterpret_cast<void**>(&p->owned[x]), bytes) != cudaSuccess) {
+                set_last_error("cudaMalloc of a plan arena failed");
+                return COSMA_B200_OUT_OF_MEMORY;
+            }
+        }
+    const bool beta_zero = beta[0] == 0.0 && (p->elem_doubles == 1 || beta[1] == 0.0);
+    const void* host_in[3] = {A, B, C};
+    for (int x = 0; x < 3; ++x) {
+        if (x == 2 && beta_zero) continue;
+        const size_t bytes = p->schedule.initial_elements(x) * es;
+        if (bytes && cudaMemcpyAsync(p->owned[x], host_in[x], bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return COSMA_B200_CUDA_ERROR;
+    }
+    int rc = cosma_b200_multiply(plan, alpha, beta, p->owned[0], p->owned[1], p->owned[2], stream);
+    if (rc != COSMA_B200_OK) return rc;
+    const size_t cbytes = p->schedule.initial_elements(2) * es;
+    if (cbytes && cudaMemcpyAsync(C, p->owned[2], cbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+    return COSMA_B200_OK;
 }
 
 int cosma_b200_plan_last_launches(void* plan) { return static_cast<Plan*>(plan)->last_launches; }

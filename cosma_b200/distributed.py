@@ -32,6 +32,7 @@ def _declare(lib):
     lib.cosma_b200_plan_export.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(i64)]
     lib.cosma_b200_plan_local_blocks.argtypes = [vp, ci, ci, ctypes.POINTER(ci), ci, ctypes.POINTER(ci)]
     lib.cosma_b200_multiply.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp, vp, vp, vp]
+    lib.cosma_b200_multiply_host.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp, vp, vp, vp]
     lib.cosma_b200_plan_last_launches.argtypes = [vp]
     lib.cosma_b200_plan_time_gemms.argtypes = [vp, ci]
     lib.cosma_b200_plan_gemm_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci, ctypes.POINTER(ci)]
@@ -167,6 +168,19 @@ class MultiplyPlan:
         _lib.check(st, "cosma_b200_multiply")
         return self.lib.cosma_b200_plan_last_launches(self.handle)
 
+    def multiply_host(self, hA, hB, hC, alpha=1.0, beta=0.0, stream=None):
+        """hA, hB, hC: pinned host tensors holding the rank's local matrices (reference layout)."""
+        import torch
+        if self.dtype == "d":
+            al = (ctypes.c_double * 1)(float(alpha)); be = (ctypes.c_double * 1)(float(beta))
+        else:
+            al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+            be = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
+        s = stream if stream is not None else torch.cuda.current_stream()
+        st = self.lib.cosma_b200_multiply_host(self.handle, al, be, ctypes.c_void_p(hA.data_ptr()), ctypes.c_void_p(hB.data_ptr()),
+                                               ctypes.c_void_p(hC.data_ptr()), ctypes.c_void_p(s.cuda_stream))
+        _lib.check(st, "cosma_b200_multiply_host")
+
     def time_gemms(self, enable=True):
         self.lib.cosma_b200_plan_time_gemms(self.handle, 1 if enable else 0)
 
@@ -202,3 +216,53 @@ def gather_local_to_global(plan, label, local, full, rank=None):
         full[r0:r1 + 1, c0:c1 + 1] = local[pos:pos + nr * nc].reshape(nc, nr).T
         pos += nr * nc
     return pos
+
+
+class MultiplyJob:
+    """bench.py's N > 1 workload: one cosma::multiply of (m, n, k) over `world` GPUs with the automatic strategy,
+    synthetic U[0,10) local matrices (the reference miniapp's fill, miniapp/cosma_miniapp.cpp:21-25,64-70)."""
+
+    def __init__(self, m, n, k, world, rank, device, steps=""):
+        import torch
+        self.comm = init_comm(device)
+        self.plan = MultiplyPlan(self.comm, m, n, k, steps, "d", device=device)
+        self.strategy_string = self.plan.strategy
+        gen = torch.Generator(device=device)
+        gen.manual_seed(rank)
+        for mat in (self.plan.A, self.plan.B):
+            if mat.initial:
+                mat.local.copy_(torch.rand(mat.initial, device=device, dtype=torch.float64, generator=gen) * 10)
+        self.plan.C.local.fill_(float("nan"))
+        self.plan.time_gemms(True)
+        ops = [op for op in self.plan.ops() if op["kind"] == "gemm"]
+        self.flops_per_local_gemm = sum(2.0 * op["m"] * op["n"] * op["k"] for op in ops) / max(len(ops), 1)
+        self.device = device
+
+    def run(self):
+        return self.plan.multiply(1.0, 0.0)
+
+    def mean_gemm_ms(self):
+        t = self.plan.gemm_times_ms()
+        return sum(t) / max(len(t), 1)
+
+    def e2e(self, reps):
+        """Same multiply through the host-pointer entry point: pinned local A, B in, local C out, per step."""
+        import torch
+        import torch.distributed as dist
+        pl = self.plan
+        hA = torch.empty(max(pl.initial_elements[0], 1), dtype=torch.float64).pin_memory(); hA[:pl.initial_elements[0]].copy_(pl.A.local)
+        hB = torch.empty(max(pl.initial_elements[1], 1), dtype=torch.float64).pin_memory(); hB[:pl.initial_elements[1]].copy_(pl.B.local)
+        hC = torch.empty(max(pl.initial_elements[2], 1), dtype=torch.float64).pin_memory()
+        pl.multiply_host(hA, hB, hC); torch.cuda.synchronize(); dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            pl.multiply_host(hA, hB, hC)
+        e1.record(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=self.device, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ok = bool(torch.equal(hC[:1024], pl.C.local[:1024].cpu())) if pl.initial_elements[2] else True
+        return {"value": 2.0 * pl.m * pl.n * pl.k / (ms.item() * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                "h2d_bytes_per_step": 8 * (pl.initial_elements[0] + pl.initial_elements[1]), "d2h_bytes_per_step": 8 * pl.initial_elements[2],
+                "ms_per_step": ms.item(), "api": "cosma_b200_multiply_host (pinned host local A,B -> local C, per rank)",
+                "matches_device_path": ok}

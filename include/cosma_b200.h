@@ -101,6 +101,10 @@ COSMA_B200_API int cosma_b200_plan_local_blocks(void* plan, int matrix, int rank
  * beta: host pointers (1 double, or 2 for 'z'). Asynchronous on `stream`. Idle ranks return immediately. */
 COSMA_B200_API int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, void* A, void* B, void* C,
                                        void* stream);
+/* Same with HOST local matrices (pinned for asynchrony): H2D of local A, B (C too when beta != 0) into arenas owned by
+ * the plan, run, D2H of local C. The reference's calling convention (host-resident CosmaMatrix buffers). */
+COSMA_B200_API int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta, const void* A, const void* B,
+                                            void* C, void* stream);
 COSMA_B200_API int cosma_b200_plan_last_launches(void* plan);                  /* GEMM kernels launched by the last run */
 COSMA_B200_API int cosma_b200_plan_time_gemms(void* plan, int enable);         /* record CUDA events around each GEMM */
 COSMA_B200_API int cosma_b200_plan_gemm_times(void* plan, float* out_ms, int cap, int* n);
