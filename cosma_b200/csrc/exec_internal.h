@@ -1,0 +1,78 @@
+// Internal types shared by the executors (multiply_exec.cu, transform_exec.cu, layout_multiply.cu).
+#pragma once
+#include "../../include/cosma_b200.h"
+#include "nccl_dyn.h"
+#include "relayout_sm100.h"
+
+#include <cosma/schedule.hpp>
+#include <costa/transform.hpp>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace cosma_b200 {
+void set_last_error(const std::string& msg);
+
+struct LayoutMultiplyState;  // layout_multiply.cu
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, size = 1;
+    // state cached across ?multiply_using_layout / p?gemm calls on this communicator (the reference caches the
+    // communicator + strategy in its context, context.cpp:80-125); destroyed with the communicator
+    std::map<std::string, LayoutMultiplyState*> layout_states;
+    ~Comm();
+};
+
+struct Plan {
+    cosma::Schedule schedule;
+    char dtype = 'd';
+    int elem_doubles = 1;  // doubles per element: 1 (d) or 2 (z)
+    std::vector<ncclComm_t> ring_comms;  // by Schedule::rings() index
+    int last_launches = 0;
+    std::vector<float> gemm_ms;  // optional per-GEMM timing of the last run
+    std::vector<cudaEvent_t> ev;
+    bool time_gemms = false;
+    // library-owned device arenas for the host-pointer entry point (allocated on first use)
+    double* owned[3] = {nullptr, nullptr, nullptr};
+};
+
+int plan_run(Plan& plan, const double* alpha, const double* beta, double* A, double* B, double* C, cudaStream_t stream);
+
+// costa::transform on the device: pack kernel -> grouped ncclSend/ncclRecv -> unpack kernel
+struct TransformPlan {
+    costa::transform_plan host;
+    char dtype = 'd';
+    Comm* comm = nullptr;
+    char* send_buf = nullptr;
+    char* recv_buf = nullptr;
+    RelayoutBatch stage1;  // pack + local pieces
+    RelayoutBatch stage2;  // unpack pieces
+    int last_launches = 0;
+    ~TransformPlan();
+};
+// Builds the device plan (allocates buffers, uploads piece lists). comm may be null (planning only / single rank).
+int transform_plan_build(Comm* comm, int rank, int nranks, char dtype, const std::vector<costa::transform_spec>& specs,
+                         std::unique_ptr<TransformPlan>& out);
+int transform_plan_run(TransformPlan& plan, cudaStream_t stream);
+
+#define COSMA_B200_NCCL_TRY(call)                                                                        \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess) {                                                                         \
+            ::cosma_b200::set_last_error(std::string(#call) + ": " + ::cosma_b200::nccl()->GetErrorString(r_)); \
+            return COSMA_B200_NCCL_ERROR;                                                                \
+        }                                                                                                \
+    } while (0)
+#define COSMA_B200_CUDA_TRY(call)                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            ::cosma_b200::set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_));            \
+            return COSMA_B200_CUDA_ERROR;                                                                \
+        }                                                                                                \
+    } while (0)
+
+}  // namespace cosma_b200

@@ -1,0 +1,394 @@
+// multiply_using_layout and p?gemm on the device.
+//
+//   cosma::multiply_using_layout (reference src/cosma/multiply.cpp:78-213; C interface cinterface.cpp:54-150)
+//   cosma::pxgemm               (reference src/cosma/cosma_pxgemm.cpp:16-388; ScaLAPACK symbols pxgemm.cpp:8-136)
+//
+// Same three phases as the reference: (1) COSTA-transform op(A), op(B) from the caller's layout into COSMA's native
+// layout with alpha = 1, beta = 0; (2) cosma::multiply with alpha = 1, beta = 0; (3) COSTA-transform the COSMA-layout
+// result into the caller's C with the caller's (alpha, beta). alpha, beta and op() are applied by the relayout kernels,
+// never by the GEMM (multiply.cpp:186-204). Everything is resident in HBM and queued on one stream; the strategy, ring
+// communicators, arenas and transform plans are cached per communicator (the reference caches communicator+strategy in
+// its context, context.cpp:80-125, and re-derives the COSTA messages on every call).
+#include "exec_internal.h"
+
+#include <costa/layout.hpp>
+
+#include <cstring>
+
+namespace cosma_b200 {
+
+costa::grid_layout layout_from_c(const cosma_b200_layout& l, char ordering, int nranks);  // transform_exec.cu
+
+struct LayoutMultiplyState {
+    void* plan = nullptr;  // cosma_b200 multiply plan (Plan*)
+    char dtype = 'd';
+    char* arena[3] = {nullptr, nullptr, nullptr};
+    costa::grid_layout native[3];  // COSMA layouts of A, B, C with blocks pointing into the arenas
+    struct Entry {
+        std::string key;
+        std::unique_ptr<TransformPlan> in, out;
+        std::uint64_t stamp = 0;
+    };
+    std::vector<Entry> transforms;  // small LRU of transform plans keyed by the caller's layouts
+    std::uint64_t clock = 0;
+    int last_launches = 0;
+    ~LayoutMultiplyState() {
+        transforms.clear();
+        for (auto& a : arena)
+            if (a) cudaFree(a);
+        if (plan) cosma_b200_plan_destroy(plan);
+    }
+};
+
+Comm::~Comm() {
+    for (auto& kv : layout_states) delete kv.second;
+}
+
+namespace {
+
+constexpr size_t kMaxCachedTransforms = 8;
+
+// process grid of a ScaLAPACK-style call: what BLACS would answer for the context in desc[1]
+// (reference blacs.hpp:5-35, scalapack.cpp:3-46)
+struct Grid {
+    Comm* comm = nullptr;
+    char order = 'R';
+    int nprow = 1, npcol = 1;
+    // device staging for host-resident operands (N4), grown on demand
+    char* stage[3] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes[3] = {0, 0, 0};
+    ~Grid() {
+        for (auto& s : stage)
+            if (s) cudaFree(s);
+    }
+};
+
+void append(std::string& key, const void* p, size_t n) { key.append(static_cast<const char*>(p), n); }
+
+void append_layout(std::string& key, const costa::grid_layout& l) {
+    append(key, l.grid.grid.rows_split.data(), l.grid.grid.rows_split.size() * sizeof(int));
+    append(key, l.grid.grid.cols_split.data(), l.grid.grid.cols_split.size() * sizeof(int));
+    append(key, l.grid.owners.data(), l.grid.owners.size() * sizeof(int));
+    for (const auto& b : l.blocks) {
+        append(key, &b.bi, sizeof(int));
+        append(key, &b.bj, sizeof(int));
+        append(key, &b.data, sizeof(void*));
+        append(key, &b.ld, sizeof(b.ld));
+    }
+    key.push_back(l.ordering);
+    key.push_back('|');
+}
+
+bool is_zero(const double* v, bool cplx) { return v[0] == 0.0 && (!cplx || v[1] == 0.0); }
+
+// C = beta * C on the caller's layout (grid_layout::scale_by, reference grid_layout.hpp:55-63); beta == 0 stores zeros
+int scale_layout(char dtype, const costa::grid_layout& C, const double* beta, cudaStream_t stream) {
+    const bool cplx = dtype == 'c' || dtype == 'z';
+    if (beta[0] == 1.0 && (!cplx || beta[1] == 0.0)) return COSMA_B200_OK;
+    std::vector<costa::piece> ps;
+    for (const auto& b : C.blocks) {
+        costa::piece p;
+        p.n_rows = C.grid.grid.rows_split[b.bi + 1] - C.grid.grid.rows_split[b.bi];
+        p.n_cols = C.grid.grid.cols_split[b.bj + 1] - C.grid.grid.cols_split[b.bj];
+        p.src = b.data; p.dst = b.data;
+        p.src_ld = p.dst_ld = b.ld;
+        p.src_ordering = p.dst_ordering = C.ordering;
+        p.scale_only = true;
+        p.transform = 0;
+        ps.push_back(p);
+    }
+    std::vector<costa::transform_spec> specs(1);
+    specs[0].alpha[0] = 0.0; specs[0].alpha[1] = 0.0;
+    specs[0].beta[0] = beta[0]; specs[0].beta[1] = cplx ? beta[1] : 0.0;
+    std::vector<DevPiece> dev;
+    std::vector<DevScalars> scalars;
+    RelayoutBatch batch;
+    relayout_normalise(ps, nullptr, nullptr, dtype_bytes(dtype), specs, dev, scalars, &batch.total_tiles, &batch.elements, &batch.reads_dst);
+    int st = relayout_upload(dev, scalars, batch);
+    if (st == COSMA_B200_OK) st = relayout_launch(batch, dtype, stream);
+    if (batch.d_pieces) cudaStreamSynchronize(stream);
+    relayout_free(batch);
+    return st;
+}
+
+int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, LayoutMultiplyState** out) {
+    const std::string key = std::string(1, dtype) + ":" + std::to_string(m) + ":" + std::to_string(n) + ":" + std::to_string(k) + ":" + (steps ? steps : "");
+    auto it = c->layout_states.find(key);
+    if (it != c->layout_states.end()) {
+        *out = it->second;
+        return COSMA_B200_OK;
+    }
+    auto st = std::make_unique<LayoutMultiplyState>();
+    st->dtype = dtype;
+    int rc = cosma_b200_plan_create(c, c->rank, c->size, m, n, k, steps ? steps : "", dtype, &st->plan);
+    if (rc != COSMA_B200_OK) return rc;
+    Plan* plan = static_cast<Plan*>(st->plan);
+    const int eb = dtype_bytes(dtype);
+    const int P = static_cast<int>(plan->schedule.strategy().P);
+    for (int x = 0; x < 3; ++x) {
+        const size_t bytes = std::max<std::int64_t>(plan->schedule.arena_elements(x), 1) * eb;
+        if (cudaMalloc(reinterpret_cast<void**>(&st->arena[x]), bytes) != cudaSuccess) {
+            set_last_error("multiply_using_layout: cudaMalloc of a COSMA arena failed");
+            return COSMA_B200_OUT_OF_MEMORY;
+        }
+        // the COSMA layout as a COSTA grid (reference Mapper::get_layout_grid, mapper.cpp:369-414, and
+        // CosmaMatrix::get_grid_layout, matrix.cpp:393-429: one column-major block per Mapper block, ld = rows)
+        const cosma::Mapper& mapper = plan->schedule.mapper(x);
+        costa::grid_layout& L = st->native[x];
+        L.ordering = 'C';
+        L.grid.grid.rows_split = mapper.row_split();
+        L.grid.grid.cols_split = mapper.col_split();
+        L.grid.n_ranks = c->size;
+        const auto owners = mapper.grid_owners();
+        const int nr = L.grid.grid.n_rows(), nc = L.grid.grid.n_cols();
+        L.grid.owners.resize(static_cast<size_t>(nr) * nc);
+        for (int i = 0; i < nr; ++i)
+            for (int j = 0; j < nc; ++j) L.grid.owners[static_cast<size_t>(i) * nc + j] = owners[i][j];
+        if (c->rank < P) {
+            const auto& blocks = mapper.initial_layout(c->rank);
+            const auto& offs = mapper.blocks_offsets(c->rank);
+            for (size_t b = 0; b < blocks.size(); ++b) {
+                const auto& rs = L.grid.grid.rows_split;
+                const auto& cs = L.grid.grid.cols_split;
+                const int bi = static_cast<int>(std::upper_bound(rs.begin(), rs.end(), blocks[b].rows.first()) - rs.begin()) - 1;
+                const int bj = static_cast<int>(std::upper_bound(cs.begin(), cs.end(), blocks[b].cols.first()) - cs.begin()) - 1;
+                L.blocks.push_back(costa::local_block{bi, bj, st->arena[x] + static_cast<std::int64_t>(offs[b]) * eb,
+                                                      static_cast<std::int64_t>(blocks[b].rows.length())});
+            }
+        }
+    }
+    *out = st.get();
+    c->layout_states[key] = st.release();
+    return COSMA_B200_OK;
+}
+
+int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, const double* alpha, const double* beta,
+                    const costa::grid_layout& A, const costa::grid_layout& B, const costa::grid_layout& C, const char* steps,
+                    cudaStream_t stream, int* launches) {
+    const bool cplx = dtype == 'c' || dtype == 'z';
+    if (launches) *launches = 0;
+    // corner cases allowed by the BLAS standard (multiply.cpp:96-109, cosma_pxgemm.cpp:36-46)
+    if (m == 0 || n == 0) return COSMA_B200_OK;
+    if (k == 0 || is_zero(alpha, cplx)) return scale_layout(dtype, C, beta, stream);
+    if (dtype != 'd' && dtype != 'z') {
+        set_last_error("multiply_using_layout: only 'd' and 'z' have a GEMM kernel in this build");
+        return COSMA_B200_NOT_SUPPORTED;
+    }
+    LayoutMultiplyState* st = nullptr;
+    int rc = get_state(c, dtype, m, n, k, steps, &st);
+    if (rc != COSMA_B200_OK) return rc;
+
+    std::string key;
+    key.push_back(ta); key.push_back(tb);
+    append(key, alpha, 2 * sizeof(double));
+    append(key, beta, 2 * sizeof(double));
+    append_layout(key, A);
+    append_layout(key, B);
+    append_layout(key, C);
+    LayoutMultiplyState::Entry* entry = nullptr;
+    for (auto& e : st->transforms)
+        if (e.key == key) entry = &e;
+    if (!entry) {
+        if (st->transforms.size() >= kMaxCachedTransforms) {
+            size_t oldest = 0;
+            for (size_t i = 1; i < st->transforms.size(); ++i)
+                if (st->transforms[i].stamp < st->transforms[oldest].stamp) oldest = i;
+            // the evicted plans may still be running on the stream
+            cudaStreamSynchronize(stream);
+            st->transforms.erase(st->transforms.begin() + oldest);
+        }
+        LayoutMultiplyState::Entry e;
+        e.key = key;
+        std::vector<costa::transform_spec> in(2), out(1);
+        in[0].from = &A; in[0].to = &st->native[0]; in[0].op = ta;
+        in[1].from = &B; in[1].to = &st->native[1]; in[1].op = tb;
+        out[0].from = &st->native[2]; out[0].to = &C; out[0].op = 'N';
+        out[0].alpha[0] = alpha[0]; out[0].alpha[1] = cplx ? alpha[1] : 0.0;
+        out[0].beta[0] = beta[0]; out[0].beta[1] = cplx ? beta[1] : 0.0;
+        rc = transform_plan_build(c, c->rank, c->size, dtype, in, e.in);
+        if (rc != COSMA_B200_OK) return rc;
+        rc = transform_plan_build(c, c->rank, c->size, dtype, out, e.out);
+        if (rc != COSMA_B200_OK) return rc;
+        st->transforms.push_back(std::move(e));
+        entry = &st->transforms.back();
+    }
+    entry->stamp = ++st->clock;
+
+    rc = transform_plan_run(*entry->in, stream);
+    if (rc != COSMA_B200_OK) return rc;
+    const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+    rc = cosma_b200_multiply(st->plan, one, zero, st->arena[0], st->arena[1], st->arena[2], stream);
+    if (rc != COSMA_B200_OK) return rc;
+    rc = transform_plan_run(*entry->out, stream);
+    if (rc != COSMA_B200_OK) return rc;
+    st->last_launches = entry->in->last_launches + entry->out->last_launches + cosma_b200_plan_last_launches(st->plan);
+    if (launches) *launches = st->last_launches;
+    return COSMA_B200_OK;
+}
+
+bool is_host_pointer(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeUnregistered;
+}
+
+}  // namespace
+}  // namespace cosma_b200
+
+using namespace cosma_b200;
+
+extern "C" {
+
+static int xmultiply_using_layout(void* comm, char dtype, const char* transa, const char* transb, const double* alpha,
+                                  const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                  const cosma_b200_layout* C, void* stream) {
+    Comm* c = static_cast<Comm*>(comm);
+    if (!c || !transa || !transb || !alpha || !beta || !A || !B || !C) return COSMA_B200_INVALID_ARG;
+    try {
+        const char ta = std::toupper(*transa), tb = std::toupper(*transb);
+        const costa::grid_layout LA = layout_from_c(*A, 'C', c->size), LB = layout_from_c(*B, 'C', c->size),
+                                 LC = layout_from_c(*C, 'C', c->size);
+        const int m = LC.num_rows(), n = LC.num_cols();
+        const int k = ta == 'N' ? LA.num_cols() : LA.num_rows();
+        const double a2[2] = {alpha[0], (dtype == 'c' || dtype == 'z') ? alpha[1] : 0.0};
+        const double b2[2] = {beta[0], (dtype == 'c' || dtype == 'z') ? beta[1] : 0.0};
+        return layout_multiply(c, dtype, ta, tb, m, n, k, a2, b2, LA, LB, LC, "", static_cast<cudaStream_t>(stream), nullptr);
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+int cosma_b200_dmultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
+                                      const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                      const cosma_b200_layout* C, void* stream) {
+    return xmultiply_using_layout(comm, 'd', transa, transb, alpha, A, B, beta, C, stream);
+}
+int cosma_b200_zmultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
+                                      const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                      const cosma_b200_layout* C, void* stream) {
+    return xmultiply_using_layout(comm, 'z', transa, transb, alpha, A, B, beta, C, stream);
+}
+
+int cosma_b200_grid_create(void* comm, char order, int nprow, int npcol, void** grid_out) {
+    Comm* c = static_cast<Comm*>(comm);
+    if (!c || !grid_out || nprow < 1 || npcol < 1 || nprow * npcol > c->size) {
+        set_last_error("grid_create: need a communicator and nprow*npcol <= its size");
+        return COSMA_B200_INVALID_ARG;
+    }
+    order = std::toupper(order);
+    if (order != 'R' && order != 'C') return COSMA_B200_INVALID_ARG;
+    auto* g = new Grid;
+    g->comm = c;
+    g->order = order;
+    g->nprow = nprow;
+    g->npcol = npcol;
+    *grid_out = g;
+    return COSMA_B200_OK;
+}
+int cosma_b200_grid_destroy(void* grid) {
+    delete static_cast<Grid*>(grid);
+    return COSMA_B200_OK;
+}
+int cosma_b200_grid_info(void* grid, int* nprow, int* npcol, int* myrow, int* mycol) {
+    Grid* g = static_cast<Grid*>(grid);
+    if (!g) return COSMA_B200_INVALID_ARG;
+    if (nprow) *nprow = g->nprow;
+    if (npcol) *npcol = g->npcol;
+    int r = -1, cc = -1;
+    if (g->comm->rank < g->nprow * g->npcol) costa::rank_to_grid(g->comm->rank, g->nprow, g->npcol, g->order, &r, &cc);
+    if (myrow) *myrow = r;
+    if (mycol) *mycol = cc;
+    return COSMA_B200_OK;
+}
+
+// descriptor fields (reference scalapack.hpp:11-47): [2] M, [3] N, [4] MB, [5] NB, [6] RSRC, [7] CSRC, [8] LLD
+static int xpgemm(void* grid, char dtype, char transa, char transb, int m, int n, int k, const double* alpha, const void* a, int ia,
+                  int ja, const int* desca, const void* b, int ib, int jb, const int* descb, const double* beta, void* c, int ic, int jc,
+                  const int* descc, void* stream_v) {
+    Grid* g = static_cast<Grid*>(grid);
+    if (!g || !alpha || !beta || !desca || !descb || !descc) return COSMA_B200_INVALID_ARG;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    try {
+        const bool cplx = dtype == 'c' || dtype == 'z';
+        const int eb = dtype_bytes(dtype);
+        if (eb == 0) return COSMA_B200_INVALID_ARG;
+        const char ta = std::toupper(transa), tb = std::toupper(transb);
+        if (m == 0 || n == 0) return COSMA_B200_OK;
+        const int a_subm = ta == 'N' ? m : k, a_subn = ta == 'N' ? k : m;
+        const int b_subm = tb == 'N' ? k : n, b_subn = tb == 'N' ? n : k;
+        const int rank = g->comm->rank;
+        const bool in_grid = rank < g->nprow * g->npcol;
+        int myrow = 0, mycol = 0;
+        if (in_grid) costa::rank_to_grid(rank, g->nprow, g->npcol, g->order, &myrow, &mycol);
+
+        // host-resident operands (what a ScaLAPACK application passes): stage the rank's local arrays through HBM
+        const void* user[3] = {a, b, c};
+        const int* desc[3] = {desca, descb, descc};
+        void* dev[3] = {const_cast<void*>(a), const_cast<void*>(b), c};
+        bool staged[3] = {false, false, false};
+        size_t local_bytes[3] = {0, 0, 0};
+        const bool scale_only = k == 0 || is_zero(alpha, cplx);
+        const bool c_whole = ic == 1 && jc == 1 && m == descc[2] && n == descc[3];
+        for (int x = 0; x < 3; ++x) {
+            if (!in_grid || !user[x]) continue;
+            if (scale_only && x < 2) continue;
+            if (!is_host_pointer(user[x])) continue;
+            const int loc_cols = costa::numroc(desc[x][3], desc[x][5], mycol, desc[x][7], g->npcol);
+            local_bytes[x] = static_cast<size_t>(desc[x][8]) * std::max(loc_cols, 0) * eb;
+            if (local_bytes[x] == 0) continue;
+            if (g->stage_bytes[x] < local_bytes[x]) {
+                if (g->stage[x]) { cudaStreamSynchronize(stream); cudaFree(g->stage[x]); g->stage[x] = nullptr; g->stage_bytes[x] = 0; }
+                if (cudaMalloc(reinterpret_cast<void**>(&g->stage[x]), local_bytes[x]) != cudaSuccess) {
+                    set_last_error("p?gemm: cudaMalloc of a staging buffer failed");
+                    return COSMA_B200_OUT_OF_MEMORY;
+                }
+                g->stage_bytes[x] = local_bytes[x];
+            }
+            staged[x] = true;
+            dev[x] = g->stage[x];
+            // C is uploaded unless it is overwritten completely (beta == 0 on the whole matrix)
+            const bool upload = x < 2 || !(is_zero(beta, cplx) && c_whole);
+            if (upload) COSMA_B200_CUDA_TRY(cudaMemcpyAsync(dev[x], user[x], local_bytes[x], cudaMemcpyHostToDevice, stream));
+        }
+
+        auto layout_of = [&](int x, int i0, int j0, int sm, int sn) {
+            return costa::get_scalapack_layout(desc[x][8], desc[x][2], desc[x][3], i0, j0, sm, sn, desc[x][4], desc[x][5], g->nprow, g->npcol,
+                                               g->order, desc[x][6], desc[x][7], dev[x], eb, 'C', in_grid ? rank : -1);
+        };
+        const double a2[2] = {alpha[0], cplx ? alpha[1] : 0.0}, b2[2] = {beta[0], cplx ? beta[1] : 0.0};
+        int rc;
+        if (scale_only) {
+            costa::grid_layout LC = layout_of(2, ic, jc, m, n);
+            LC.grid.n_ranks = g->comm->size;
+            rc = scale_layout(dtype, LC, b2, stream);
+        } else {
+            costa::grid_layout LA = layout_of(0, ia, ja, a_subm, a_subn), LB = layout_of(1, ib, jb, b_subm, b_subn),
+                               LC = layout_of(2, ic, jc, m, n);
+            LA.grid.n_ranks = LB.grid.n_ranks = LC.grid.n_ranks = g->comm->size;
+            rc = layout_multiply(g->comm, dtype, ta, tb, m, n, k, a2, b2, LA, LB, LC, "", stream, nullptr);
+        }
+        if (rc != COSMA_B200_OK) return rc;
+        if (staged[2]) COSMA_B200_CUDA_TRY(cudaMemcpyAsync(c, dev[2], local_bytes[2], cudaMemcpyDeviceToHost, stream));
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+int cosma_b200_pdgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const double* a, int ia, int ja,
+                      const int* desca, const double* b, int ib, int jb, const int* descb, const double* beta, double* c, int ic, int jc,
+                      const int* descc, void* stream) {
+    return xpgemm(grid, 'd', transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib, jb, descb, beta, c, ic, jc, descc, stream);
+}
+int cosma_b200_pzgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const double* a, int ia, int ja,
+                      const int* desca, const double* b, int ib, int jb, const int* descb, const double* beta, double* c, int ic, int jc,
+                      const int* descc, void* stream) {
+    return xpgemm(grid, 'z', transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib, jb, descb, beta, c, ic, jc, descc, stream);
+}
+
+}  // extern "C"

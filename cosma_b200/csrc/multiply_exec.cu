@@ -3,37 +3,12 @@
 // (the reference's communicator::create_communicators, communicator.cpp:282-308, and gpu::nccl_copy / nccl_reduce,
 // gpu/nccl_utils.cpp:45-280, which stage through host memory around every collective); local compute = the sm_100a
 // DGEMM/ZGEMM kernels. Operands never leave HBM.
-#include "../../include/cosma_b200.h"
+#include "exec_internal.h"
 #include "gemm_f64_sm100.h"
-#include "nccl_dyn.h"
-
-#include <cosma/schedule.hpp>
 
 #include <cstring>
-#include <memory>
-#include <string>
-#include <vector>
 
 namespace cosma_b200 {
-void set_last_error(const std::string& msg);
-
-struct Comm {
-    ncclComm_t comm = nullptr;
-    int rank = 0, size = 1;
-};
-
-struct Plan {
-    cosma::Schedule schedule;
-    char dtype = 'd';
-    int elem_doubles = 1;  // doubles per element: 1 (d) or 2 (z)
-    std::vector<ncclComm_t> ring_comms;  // by Schedule::rings() index
-    int last_launches = 0;
-    std::vector<float> gemm_ms;  // optional per-GEMM timing of the last run
-    std::vector<cudaEvent_t> ev;
-    bool time_gemms = false;
-    // library-owned device arenas for the host-pointer entry point (allocated on first use)
-    double* owned[3] = {nullptr, nullptr, nullptr};
-};
 
 namespace {
 
@@ -67,22 +42,8 @@ __global__ void axpby_kernel(int64_t n, double br, double bi, double* __restrict
     }
 }
 
-#define NCCL_TRY(call)                                                                     \
-    do {                                                                                   \
-        ncclResult_t r_ = (call);                                                          \
-        if (r_ != ncclSuccess) {                                                           \
-            set_last_error(std::string(#call) + ": " + nccl()->GetErrorString(r_));        \
-            return COSMA_B200_NCCL_ERROR;                                                  \
-        }                                                                                  \
-    } while (0)
-#define CUDA_TRY(call)                                                                     \
-    do {                                                                                   \
-        cudaError_t e_ = (call);                                                           \
-        if (e_ != cudaSuccess) {                                                           \
-            set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_));            \
-            return COSMA_B200_CUDA_ERROR;                                                  \
-        }                                                                                  \
-    } while (0)
+#define NCCL_TRY COSMA_B200_NCCL_TRY
+#define CUDA_TRY COSMA_B200_CUDA_TRY
 
 int run_allgather(const Plan& plan, const cosma::ScheduleOp& op, double* arena, cudaStream_t stream) {
     const NcclApi* N = nccl();
@@ -237,13 +198,18 @@ int cosma_b200_nccl_unique_id(uint8_t* out128) {
 }
 
 int cosma_b200_comm_create(int rank, int nranks, const uint8_t* id128, void** comm_out) {
-    const auto* N = nccl();
-    if (!N) return COSMA_B200_NCCL_ERROR;
-    ncclUniqueId id;
-    std::memcpy(&id, id128, 128);
+    if (!comm_out || nranks < 1 || rank < 0 || rank >= nranks) return COSMA_B200_INVALID_ARG;
     auto c = std::make_unique<Comm>();
     c->rank = rank;
     c->size = nranks;
+    if (nranks == 1) {  // single-rank job: nothing to exchange, NCCL is not needed (id128 may be NULL)
+        *comm_out = c.release();
+        return COSMA_B200_OK;
+    }
+    const auto* N = nccl();
+    if (!N || !id128) return COSMA_B200_NCCL_ERROR;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
     ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
     if (r != ncclSuccess) {
         set_last_error(std::string("ncclCommInitRank: ") + N->GetErrorString(r));

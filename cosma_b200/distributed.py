@@ -58,7 +58,9 @@ def init_comm(device=None):
     lib = _lib.load()
     _declare(lib)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return Comm(None, 0, 1)
+        handle = ctypes.c_void_p()
+        _lib.check(lib.cosma_b200_comm_create(0, 1, None, ctypes.byref(handle)), "cosma_b200_comm_create")
+        return Comm(handle, 0, 1)
     rank, size = dist.get_rank(), dist.get_world_size()
     uid = (ctypes.c_uint8 * 128)()
     if rank == 0:

@@ -109,6 +109,107 @@ COSMA_B200_API int cosma_b200_plan_last_launches(void* plan);                  /
 COSMA_B200_API int cosma_b200_plan_time_gemms(void* plan, int enable);         /* record CUDA events around each GEMM */
 COSMA_B200_API int cosma_b200_plan_gemm_times(void* plan, float* out_ms, int cap, int* n);
 
+/* ---- COSTA relayout (R3/R4 + exchange) ------------------------------------------------------------------
+ * Layout description in the shape of the reference's C interface (src/cosma/cinterface.hpp:16-41: struct block,
+ * struct layout; libs/COSTA/src/costa/layout.hpp:14-48: block_t, custom_layout): a grid of blocks given by split
+ * points, the owner rank of every block (row-major: owners[i*colblocks + j]) and the blocks of the calling rank.
+ * `data` points at element (0,0) of the block in DEVICE memory; `ld` is its leading dimension in elements. */
+typedef struct cosma_b200_block {
+    void* data;
+    int ld;
+    int row;  /* block row index in the grid */
+    int col;  /* block column index in the grid */
+} cosma_b200_block;
+typedef struct cosma_b200_layout {
+    int rowblocks;
+    int colblocks;
+    const int* rowsplit;  /* rowblocks + 1 entries: block i covers rows [rowsplit[i], rowsplit[i+1]) */
+    const int* colsplit;
+    const int* owners;
+    int nlocalblocks;
+    cosma_b200_block* localblocks;
+} cosma_b200_layout;
+
+/* One batched launch of COSTA's kernel: dest = beta*dest + alpha*op(src) for every piece.
+ * Replaces costa::memory::copy_and_transform (libs/COSTA/src/costa/grid2grid/memory_utils.hpp:287-346), same
+ * argument meaning: n_rows x n_cols is the SOURCE block, orderings 'C' (column-major) | 'R' (row-major), ld = 0 means
+ * tight. alpha/beta: (re, im) pairs (im ignored for real dtypes). dtype: 's','d','c','z'. DEVICE pointers. With
+ * alpha = 1, beta = 0 the result is a bit-exact move; beta == 0 never reads dest. */
+typedef struct cosma_b200_piece {
+    const void* src;
+    void* dst;
+    int64_t src_ld, dst_ld;
+    int n_rows, n_cols;
+    char src_ordering, dst_ordering;
+    char transpose, conjugate;  /* 0 | 1 */
+    double alpha[2], beta[2];
+} cosma_b200_piece;
+COSMA_B200_API int cosma_b200_relayout_batch(void* stream, char dtype, int n, const cosma_b200_piece* pieces);
+
+/* costa::transform(from[], to[], trans[], alpha[], beta[], comm) (libs/COSTA/src/costa/grid2grid/transform.cpp:231-282)
+ * and costa::transformer<T>::schedule/transform (transformer.hpp:8-63), split into plan and run:
+ *   to[i] = beta[i]*to[i] + alpha[i]*op_i(from[i]),  op_i = trans[i] in 'N' | 'T' | 'C', for all i in one exchange.
+ * ordering_from/ordering_to: one char per layout ('C' | 'R'), NULL = all 'C'. alpha/beta: 2 doubles per transform.
+ * comm == NULL plans for (rank, nranks) without the ability to exchange (single rank, or tests that only export the
+ * plan). Collective over comm when executed: pack kernel -> one NCCL group of send/recv -> unpack kernel. */
+COSMA_B200_API int cosma_b200_transform_plan_create(void* comm, int rank, int nranks, char dtype, int n,
+                                                    const cosma_b200_layout* from, const cosma_b200_layout* to,
+                                                    const char* ordering_from, const char* ordering_to, const char* trans,
+                                                    const double* alpha, const double* beta, void** plan_out);
+COSMA_B200_API int cosma_b200_transform_run(void* plan, void* stream);
+COSMA_B200_API int cosma_b200_transform_plan_destroy(void* plan);
+/* Flat int64 dump of the plan for tests/tools (format: transform_exec.cu). Two-call pattern: buf == NULL -> *len. */
+COSMA_B200_API int cosma_b200_transform_plan_export(void* plan, int64_t* buf, int64_t cap, int64_t* len);
+/* Elements this rank moves per run: [0] staying on the rank, [1] sent to peers; kernels launched by the last run. */
+COSMA_B200_API int cosma_b200_transform_plan_stats(void* plan, int64_t* local_elements, int64_t* remote_elements, int* launches);
+
+/* costa::get_scalapack_layout (libs/COSTA/src/costa/grid2grid/scalapack_layout.cpp:178-285): grid, owners and the
+ * local blocks (as element offsets into the rank's local array) of sub(A) = A(ia:ia+sub_m-1, ja:ja+sub_n-1) in a
+ * block-cyclic distribution. Two-call pattern: pass NULL arrays to obtain *rowblocks, *colblocks, *nlocal. */
+COSMA_B200_API int cosma_b200_scalapack_layout(int lld, int mat_rows, int mat_cols, int ia, int ja, int sub_m, int sub_n, int mb,
+                                               int nb, int nprow, int npcol, char grid_order, int rsrc, int csrc,
+                                               char data_ordering, int rank, int* rowblocks, int* colblocks, int* rowsplit,
+                                               int* colsplit, int* owners, int* nlocal, int* local_row, int* local_col,
+                                               int64_t* local_offset);
+/* ScaLAPACK NUMROC. */
+COSMA_B200_API int cosma_b200_numroc(int n, int nb, int iproc, int isrcproc, int nprocs);
+
+/* ---- multiply on caller-defined layouts ------------------------------------------------------------------
+ * {d,z}multiply_using_layout(MPI_Comm, transa, transb, alpha, layout A, layout B, beta, layout C)
+ * (reference src/cosma/cinterface.hpp:42-76, cinterface.cpp:54-150 -> multiply_using_layout, multiply.cpp:78-213):
+ * C = alpha*op(A)*op(B) + beta*C with every matrix in its own block layout (column-major blocks, DEVICE pointers).
+ * op(A) and op(B) are moved into COSMA's native layout by the relayout kernels, multiplied with the automatic
+ * Strategy(m,n,k,P), and the result is moved into C's layout with (alpha, beta) applied on the way. Collective over
+ * `comm` (a cosma_b200 communicator handle in place of MPI_Comm). alpha/beta: 1 double ('d') or 2 ('z'). Strategy,
+ * ring communicators, arenas and transform plans are cached in the communicator across calls. */
+COSMA_B200_API int cosma_b200_dmultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
+                                                     const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                                     const cosma_b200_layout* C, void* stream);
+COSMA_B200_API int cosma_b200_zmultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
+                                                     const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                                     const cosma_b200_layout* C, void* stream);
+
+/* ---- ScaLAPACK p?gemm ------------------------------------------------------------------------------------
+ * Process grid = what BLACS answers for the context id in desc[1] (Cblacs_gridinfo / Cblacs_get; reference
+ * src/cosma/blacs.hpp:5-35, scalapack.cpp:3-46, cosma_pxgemm.cpp:57-69). BLACS does not exist on this box, so the grid
+ * is an explicit handle: order 'R' (row-major rank numbering) | 'C'; rank r of comm sits at (r / npcol, r % npcol) or
+ * (r % nprow, r / nprow). */
+COSMA_B200_API int cosma_b200_grid_create(void* comm, char order, int nprow, int npcol, void** grid_out);
+COSMA_B200_API int cosma_b200_grid_destroy(void* grid);
+COSMA_B200_API int cosma_b200_grid_info(void* grid, int* nprow, int* npcol, int* myrow, int* mycol);
+/* pdgemm_ / pzgemm_ (reference src/cosma/pxgemm.h:6-107 -> cosma::pxgemm<T>, cosma_pxgemm.cpp:16-388):
+ * sub(C) = alpha*op(sub(A))*op(sub(B)) + beta*sub(C) on 2D block-cyclic matrices. desc = the 9-int ScaLAPACK descriptor
+ * ([2] M, [3] N, [4] MB, [5] NB, [6] RSRC, [7] CSRC, [8] LLD; [1], the BLACS context, is ignored in favour of `grid`);
+ * ia, ja, ... 1-based. a, b, c: the rank's local arrays, DEVICE or HOST pointers (host arrays are staged through HBM
+ * on `stream`; use pinned memory for asynchrony). beta == 0 never reads C. Corner cases as the reference
+ * (m|n = 0: return; k = 0 or alpha = 0: sub(C) *= beta). */
+COSMA_B200_API int cosma_b200_pdgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const double* a,
+                                     int ia, int ja, const int* desca, const double* b, int ib, int jb, const int* descb,
+                                     const double* beta, double* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pzgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const double* a,
+                                     int ia, int ja, const int* desca, const double* b, int ib, int jb, const int* descb,
+                                     const double* beta, double* c, int ic, int jc, const int* descc, void* stream);
+
 /* ---- local GEMM with HOST operands ('N','N') -------------------------------------------------
  * Same contract as the reference's GPU base case, which receives host pointers and streams tiles
  * through the device (gpu::gemm, libs/Tiled-MM/src/Tiled-MM/tiled_mm.cpp:492-624; copy_c_back = true).

@@ -148,3 +148,90 @@ def ref_mapper_layout(label, m, n, k, P, steps):
             pos += 1
         res.append(blocks)
     return res
+
+
+# ---- COSTA relayout ------------------------------------------------------------------------------
+
+_CAT = {"d": ("oracle_copy_and_transform_d", ctypes.c_double), "s": ("oracle_copy_and_transform_s", ctypes.c_float),
+        "i": ("oracle_copy_and_transform_i", ctypes.c_int), "z": ("oracle_copy_and_transform_z", None),
+        "c": ("oracle_copy_and_transform_c", None)}
+
+
+def copy_and_transform_raw(dtype, n_rows, n_cols, src_addr, src_ld, src_ord, dst_addr, dst_ld, dst_ord, transpose, conjugate, alpha, beta):
+    """oracle/relayout_oracle.c on raw addresses (so tests can interpret an exported transform plan piece by piece)."""
+    L = lib()
+    name, ctype = _CAT[dtype]
+    args = [i64(n_rows), i64(n_cols), ctypes.c_void_p(src_addr), i64(src_ld), ctypes.c_char(src_ord.encode()), ctypes.c_void_p(dst_addr),
+            i64(dst_ld), ctypes.c_char(dst_ord.encode()), ctypes.c_int(int(transpose)), ctypes.c_int(int(conjugate))]
+    if ctype is not None:
+        a, b = complex(alpha).real, complex(beta).real
+        getattr(L, name)(*args, ctype(int(a)) if dtype == "i" else ctype(a), ctype(int(b)) if dtype == "i" else ctype(b))
+    else:
+        npdt = np.complex128 if dtype == "z" else np.complex64
+        al = np.array([complex(alpha)], dtype=npdt); be = np.array([complex(beta)], dtype=npdt)
+        getattr(L, name)(*args, _p(al), _p(be))
+
+
+def ref_copy_and_transform(dtype, n_rows, n_cols, src, src_ld, src_ord, dst, dst_ld, dst_ord, transpose, conjugate, alpha, beta):
+    """The reference's costa::memory::copy_and_transform (memory_utils.hpp:287-346) via oracle/_ref. dtype in i,s,d,c,z."""
+    R = ref()
+    al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    be = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
+    rc = R.ref_copy_and_transform(ctypes.c_char(dtype.encode()), ctypes.c_int(n_rows), ctypes.c_int(n_cols), _p(src), ctypes.c_int(src_ld),
+                                  ctypes.c_int(1 if src_ord == "C" else 0), _p(dst), ctypes.c_int(dst_ld), ctypes.c_int(1 if dst_ord == "C" else 0),
+                                  ctypes.c_int(int(transpose)), ctypes.c_int(int(conjugate)), al, be)
+    if rc != 0:
+        raise RuntimeError("reference copy_and_transform failed (%d)" % rc)
+    return dst
+
+
+def ref_scalapack_layout(lld, mat_rows, mat_cols, ia, ja, sub_m, sub_n, mb, nb, nprow, npcol, grid_order, rsrc, csrc, data_ordering, rank):
+    """The reference's costa::get_scalapack_layout (scalapack_layout.cpp:178-285) ->
+    (rowsplit, colsplit, owners[rows][cols], [(block row, block col, element offset)])."""
+    R = ref()
+    ci = ctypes.c_int
+    nr, nc, nl = ci(), ci(), ci()
+    args = [ci(lld), ci(mat_rows), ci(mat_cols), ci(ia), ci(ja), ci(sub_m), ci(sub_n), ci(mb), ci(nb), ci(nprow), ci(npcol),
+            ctypes.c_char(grid_order.encode()), ci(rsrc), ci(csrc), ctypes.c_char(data_ordering.encode()), ci(rank)]
+    rc = R.ref_scalapack_layout(*args, ctypes.byref(nr), ctypes.byref(nc), None, None, None, ctypes.byref(nl), None, None, None)
+    if rc != 0:
+        raise RuntimeError("reference get_scalapack_layout threw")
+    rs = np.zeros(nr.value + 1, dtype=np.int32); cs = np.zeros(nc.value + 1, dtype=np.int32)
+    ow = np.zeros(max(nr.value * nc.value, 1), dtype=np.int32)
+    lr = np.zeros(max(nl.value, 1), dtype=np.int32); lc = np.zeros(max(nl.value, 1), dtype=np.int32)
+    lo = np.zeros(max(nl.value, 1), dtype=np.int64)
+    R.ref_scalapack_layout(*args, ctypes.byref(nr), ctypes.byref(nc), _p(rs), _p(cs), _p(ow), ctypes.byref(nl), _p(lr), _p(lc), _p(lo))
+    return rs, cs, ow[:nr.value * nc.value].reshape(nr.value, nc.value), [(int(lr[i]), int(lc[i]), int(lo[i])) for i in range(nl.value)]
+
+
+class _RefBlock(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("ld", ctypes.c_int), ("row", ctypes.c_int), ("col", ctypes.c_int)]
+
+
+class _RefLayout(ctypes.Structure):
+    _fields_ = [("rowblocks", ctypes.c_int), ("colblocks", ctypes.c_int), ("rowsplit", ctypes.c_void_p), ("colsplit", ctypes.c_void_p),
+                ("owners", ctypes.c_void_p), ("nlocalblocks", ctypes.c_int), ("localblocks", ctypes.POINTER(_RefBlock))]
+
+
+def ref_transform_p1(dtype, from_layout, to_layout, trans, alpha, beta):
+    """The reference's costa::transform on one rank. Layout arguments: (rowsplit, colsplit, owners, [(row, col, addr, ld)], ordering)."""
+    R = ref()
+    keep = []
+
+    def mk(l):
+        rs, cs, ow, blocks, _ = l
+        rs = np.ascontiguousarray(rs, dtype=np.int32); cs = np.ascontiguousarray(cs, dtype=np.int32)
+        ow = np.ascontiguousarray(ow, dtype=np.int32)
+        arr = (_RefBlock * max(len(blocks), 1))()
+        for i, (r, c, addr, ld) in enumerate(blocks):
+            arr[i] = _RefBlock(addr, ld, r, c)
+        keep.extend([rs, cs, ow, arr])
+        return _RefLayout(len(rs) - 1, len(cs) - 1, rs.ctypes.data, cs.ctypes.data, ow.ctypes.data, len(blocks), arr)
+
+    F, T = mk(from_layout), mk(to_layout)
+    al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    be = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
+    rc = R.ref_transform_p1(ctypes.c_char(dtype.encode()), ctypes.byref(F), ctypes.c_char(from_layout[4].encode()), ctypes.byref(T),
+                            ctypes.c_char(to_layout[4].encode()), ctypes.c_char(trans.encode()), al, be)
+    if rc != 0:
+        raise RuntimeError("reference costa::transform failed (%d)" % rc)

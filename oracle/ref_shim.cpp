@@ -164,3 +164,105 @@ extern "C" int ref_multiply_time_d(int m, int n, int k, int reps, double* times_
         return -1;
     }
 }
+
+// ---- COSTA (unmodified reference) ------------------------------------------------------------------
+#include <costa/grid2grid/memory_utils.hpp>
+#include <costa/grid2grid/scalapack_layout.hpp>
+#include <costa/grid2grid/transform.hpp>
+#include <costa/layout.hpp>
+
+namespace {
+template <typename T>
+void cat_typed(int n_rows, int n_cols, const void* src, int src_ld, int src_cm, void* dst, int dst_ld, int dst_cm, int transpose,
+               int conj, T alpha, T beta) {
+    auto& workspace = *costa::memory::get_costa_context_instance<T>();
+    costa::memory::copy_and_transform<T>(n_rows, n_cols, static_cast<const T*>(src), src_ld, src_cm != 0, static_cast<T*>(dst), dst_ld,
+                                         dst_cm != 0, transpose != 0, conj != 0, alpha, beta, workspace);
+}
+}  // namespace
+
+extern "C" {
+
+// costa::memory::copy_and_transform (memory_utils.hpp:287-346) for dtype 'i' | 's' | 'd' | 'c' | 'z'
+int ref_copy_and_transform(char dtype, int n_rows, int n_cols, const void* src, int src_ld, int src_cm, void* dst, int dst_ld, int dst_cm,
+                           int transpose, int conj, const double* alpha, const double* beta) {
+    try {
+        switch (dtype) {
+            case 'i': cat_typed<int>(n_rows, n_cols, src, src_ld, src_cm, dst, dst_ld, dst_cm, transpose, conj, (int)alpha[0], (int)beta[0]); break;
+            case 's': cat_typed<float>(n_rows, n_cols, src, src_ld, src_cm, dst, dst_ld, dst_cm, transpose, conj, (float)alpha[0], (float)beta[0]); break;
+            case 'd': cat_typed<double>(n_rows, n_cols, src, src_ld, src_cm, dst, dst_ld, dst_cm, transpose, conj, alpha[0], beta[0]); break;
+            case 'c': cat_typed<std::complex<float>>(n_rows, n_cols, src, src_ld, src_cm, dst, dst_ld, dst_cm, transpose, conj,
+                                                     std::complex<float>((float)alpha[0], (float)alpha[1]), std::complex<float>((float)beta[0], (float)beta[1])); break;
+            case 'z': cat_typed<std::complex<double>>(n_rows, n_cols, src, src_ld, src_cm, dst, dst_ld, dst_cm, transpose, conj,
+                                                      std::complex<double>(alpha[0], alpha[1]), std::complex<double>(beta[0], beta[1])); break;
+            default: return -2;
+        }
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
+
+// costa::get_scalapack_layout<double> (scalapack_layout.cpp:178-285) for an arbitrary `rank`: split points, owners
+// (row-major) and the local blocks as (block row, block col, element offset into the local array).
+int ref_scalapack_layout(int lld, int mat_rows, int mat_cols, int ia, int ja, int sub_m, int sub_n, int mb, int nb, int nprow, int npcol,
+                         char grid_order, int rsrc, int csrc, char data_ordering, int rank, int* rowblocks, int* colblocks, int* rowsplit,
+                         int* colsplit, int* owners, int* nlocal, int* local_row, int* local_col, long long* local_offset) {
+    try {
+        double* base = reinterpret_cast<double*>(std::uintptr_t(1) << 40);
+        auto ord = (grid_order == 'C' || grid_order == 'c') ? costa::scalapack::ordering::column_major : costa::scalapack::ordering::row_major;
+        auto l = costa::get_scalapack_layout<double>(lld, {mat_rows, mat_cols}, {ia, ja}, {sub_m, sub_n}, {mb, nb}, {nprow, npcol}, ord,
+                                                     {rsrc, csrc}, base, data_ordering, rank);
+        const int nr = l.grid.grid().n_rows, nc = l.grid.grid().n_cols;
+        if (rowblocks) *rowblocks = nr;
+        if (colblocks) *colblocks = nc;
+        if (nlocal) *nlocal = l.blocks.num_blocks();
+        if (rowsplit) for (int i = 0; i <= nr; ++i) rowsplit[i] = l.grid.grid().rows_split[i];
+        if (colsplit) for (int j = 0; j <= nc; ++j) colsplit[j] = l.grid.grid().cols_split[j];
+        if (owners) for (int i = 0; i < nr; ++i) for (int j = 0; j < nc; ++j) owners[i * nc + j] = l.grid.owner(i, j);
+        for (int b = 0; b < l.blocks.num_blocks(); ++b) {
+            const auto& blk = l.blocks.get_block(b);
+            if (local_row) local_row[b] = blk.coordinates.row;
+            if (local_col) local_col[b] = blk.coordinates.col;
+            if (local_offset) local_offset[b] = blk.data - base;
+        }
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
+
+// One rank (P = 1) run of costa::transform (transform.cpp:162-200): to = beta*to + alpha*op(from) between two custom
+// block layouts over the same host memory model as the C interface. Exercises the reference's grid overlay, block
+// decomposition and copy_local_blocks path. dtype 'd' | 'z'.
+struct ref_block { void* data; int ld; int row; int col; };
+struct ref_layout { int rowblocks, colblocks; const int* rowsplit; const int* colsplit; const int* owners; int nlocalblocks; ref_block* localblocks; };
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+int transform_p1(const ref_layout* from, char from_ord, const ref_layout* to, char to_ord, char trans, T alpha, T beta) {
+    auto mk = [](const ref_layout* l, char ord) {
+        std::vector<costa::block_t> blocks(l->nlocalblocks);
+        for (int i = 0; i < l->nlocalblocks; ++i) blocks[i] = costa::block_t{l->localblocks[i].data, l->localblocks[i].ld, l->localblocks[i].row, l->localblocks[i].col};
+        return costa::custom_layout<T>(l->rowblocks, l->colblocks, l->rowsplit, l->colsplit, l->owners, l->nlocalblocks, blocks.data(), ord);
+    };
+    auto F = mk(from, from_ord);
+    auto G = mk(to, to_ord);
+    costa::transform<T>(F, G, trans, alpha, beta, MPI_COMM_WORLD);
+    return 0;
+}
+}  // namespace
+
+extern "C" int ref_transform_p1(char dtype, const ref_layout* from, char from_ord, const ref_layout* to, char to_ord, char trans,
+                                const double* alpha, const double* beta) {
+    try {
+        if (dtype == 'd') return transform_p1<double>(from, from_ord, to, to_ord, trans, alpha[0], beta[0]);
+        if (dtype == 'z') return transform_p1<std::complex<double>>(from, from_ord, to, to_ord, trans, std::complex<double>(alpha[0], alpha[1]),
+                                                                   std::complex<double>(beta[0], beta[1]));
+        return -2;
+    } catch (...) {
+        return -1;
+    }
+}
