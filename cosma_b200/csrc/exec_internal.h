@@ -51,6 +51,7 @@ struct TransformPlan {
     RelayoutBatch stage1;  // pack + local pieces
     RelayoutBatch stage2;  // unpack pieces
     int last_launches = 0;
+    bool materialised = false;  // device buffers allocated and piece lists uploaded
     ~TransformPlan();
 };
 // Builds the device plan (allocates buffers, uploads piece lists). comm may be null (planning only / single rank).

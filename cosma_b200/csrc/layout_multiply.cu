@@ -100,13 +100,12 @@ int scale_layout(char dtype, const costa::grid_layout& C, const double* beta, cu
     std::vector<costa::transform_spec> specs(1);
     specs[0].alpha[0] = 0.0; specs[0].alpha[1] = 0.0;
     specs[0].beta[0] = beta[0]; specs[0].beta[1] = cplx ? beta[1] : 0.0;
-    std::vector<DevPiece> dev;
-    std::vector<DevScalars> scalars;
+    RelayoutHostList list;
     RelayoutBatch batch;
-    relayout_normalise(ps, nullptr, nullptr, dtype_bytes(dtype), specs, dev, scalars, &batch.total_tiles, &batch.elements, &batch.reads_dst);
-    int st = relayout_upload(dev, scalars, batch);
+    relayout_normalise(ps, nullptr, nullptr, dtype_bytes(dtype), specs, list);
+    int st = relayout_upload(list, batch);
     if (st == COSMA_B200_OK) st = relayout_launch(batch, dtype, stream);
-    if (batch.d_pieces) cudaStreamSynchronize(stream);
+    if (!batch.empty()) cudaStreamSynchronize(stream);
     relayout_free(batch);
     return st;
 }

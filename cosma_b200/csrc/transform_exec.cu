@@ -42,7 +42,8 @@ int transform_plan_build(Comm* comm, int rank, int nranks, char dtype, const std
 namespace {
 // device side of a plan: buffers + uploaded piece lists (separate from planning so tests can plan without a GPU)
 int materialise(TransformPlan& tp) {
-    if (tp.stage1.d_pieces || tp.stage2.d_pieces || tp.send_buf || tp.recv_buf) return COSMA_B200_OK;
+    if (tp.materialised) return COSMA_B200_OK;
+    tp.materialised = true;
     const auto& h = tp.host;
     if (h.total_send > 0 && cudaMalloc(reinterpret_cast<void**>(&tp.send_buf), h.total_send) != cudaSuccess) {
         set_last_error("transform: cudaMalloc of the send buffer failed");
@@ -52,18 +53,13 @@ int materialise(TransformPlan& tp) {
         set_last_error("transform: cudaMalloc of the receive buffer failed");
         return COSMA_B200_OUT_OF_MEMORY;
     }
-    std::vector<DevPiece> pieces;
-    std::vector<DevScalars> scalars;
-    relayout_normalise(h.pack, nullptr, tp.send_buf, h.elem_bytes, h.specs, pieces, scalars, &tp.stage1.total_tiles, &tp.stage1.elements,
-                       &tp.stage1.reads_dst);
-    relayout_normalise(h.local, nullptr, nullptr, h.elem_bytes, h.specs, pieces, scalars, &tp.stage1.total_tiles, &tp.stage1.elements,
-                       &tp.stage1.reads_dst);
-    int st = relayout_upload(pieces, scalars, tp.stage1);
+    RelayoutHostList l1, l2;
+    relayout_normalise(h.pack, nullptr, tp.send_buf, h.elem_bytes, h.specs, l1);
+    relayout_normalise(h.local, nullptr, nullptr, h.elem_bytes, h.specs, l1);
+    int st = relayout_upload(l1, tp.stage1);
     if (st != COSMA_B200_OK) return st;
-    pieces.clear();
-    relayout_normalise(h.unpack, tp.recv_buf, nullptr, h.elem_bytes, h.specs, pieces, scalars, &tp.stage2.total_tiles, &tp.stage2.elements,
-                       &tp.stage2.reads_dst);
-    return relayout_upload(pieces, scalars, tp.stage2);
+    relayout_normalise(h.unpack, tp.recv_buf, nullptr, h.elem_bytes, h.specs, l2);
+    return relayout_upload(l2, tp.stage2);
 }
 }  // namespace
 
@@ -72,9 +68,8 @@ int transform_plan_run(TransformPlan& tp, cudaStream_t stream) {
     if (st != COSMA_B200_OK) return st;
     const auto& h = tp.host;
     tp.last_launches = 0;
-    st = relayout_launch(tp.stage1, tp.dtype, stream);
+    st = relayout_launch(tp.stage1, tp.dtype, stream, &tp.last_launches);
     if (st != COSMA_B200_OK) return st;
-    tp.last_launches += tp.stage1.total_tiles > 0;
     if (h.total_send > 0 || h.total_recv > 0) {
         if (!tp.comm || !tp.comm->comm) {
             set_last_error("transform: the plan exchanges data between ranks but was created without a communicator");
@@ -90,9 +85,7 @@ int transform_plan_run(TransformPlan& tp, cudaStream_t stream) {
         }
         COSMA_B200_NCCL_TRY(N->GroupEnd());
     }
-    st = relayout_launch(tp.stage2, tp.dtype, stream);
-    tp.last_launches += tp.stage2.total_tiles > 0;
-    return st;
+    return relayout_launch(tp.stage2, tp.dtype, stream, &tp.last_launches);
 }
 
 // grid_layout from the C struct (reference grid_from_clayout, src/cosma/cinterface.cpp:10-52)
@@ -225,15 +218,14 @@ int cosma_b200_relayout_batch(void* stream, char dtype, int n, const cosma_b200_
         specs[i].alpha[0] = q.alpha[0]; specs[i].alpha[1] = (dtype == 'c' || dtype == 'z') ? q.alpha[1] : 0.0;
         specs[i].beta[0] = q.beta[0]; specs[i].beta[1] = (dtype == 'c' || dtype == 'z') ? q.beta[1] : 0.0;
     }
-    std::vector<cosma_b200::DevPiece> dev;
-    std::vector<cosma_b200::DevScalars> scalars;
+    cosma_b200::RelayoutHostList list;
     cosma_b200::RelayoutBatch b;
-    cosma_b200::relayout_normalise(ps, nullptr, nullptr, eb, specs, dev, scalars, &b.total_tiles, &b.elements, &b.reads_dst);
-    int st = cosma_b200::relayout_upload(dev, scalars, b);
+    cosma_b200::relayout_normalise(ps, nullptr, nullptr, eb, specs, list);
+    int st = cosma_b200::relayout_upload(list, b);
     if (st == COSMA_B200_OK) st = cosma_b200::relayout_launch(b, dtype, static_cast<cudaStream_t>(stream));
     // the piece list must outlive the kernel: free after the stream drains (this entry point is the convenience form;
     // plans keep their lists resident)
-    if (b.d_pieces) cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (!b.empty()) cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     cosma_b200::relayout_free(b);
     return st;
 }

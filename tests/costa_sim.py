@@ -109,3 +109,56 @@ def simulate(oracle, dtype, plans, specs):
                 recv[p][plans[p]["recv_off"][r]:plans[p]["recv_off"][r] + n] = send[r][pl["send_off"][p]:pl["send_off"][p] + n]
     for r, pl in enumerate(plans):  # stage 2: unpack
         run_pieces(oracle, dtype, pl["unpack"], specs, src_base=recv[r].ctypes.data)
+
+
+class BlockCyclic:
+    """A ScaLAPACK 2D block-cyclic matrix: per-rank local arrays (column-major, leading dimension lld) and the
+    global <-> local maps, built from the layout formulas that test_costa_cpu.py pins against the reference."""
+
+    def __init__(self, M, N, mb, nb, nprow, npcol, order="R", rsrc=0, csrc=0, lld_pad=0):
+        self.M, self.N, self.mb, self.nb = M, N, mb, nb
+        self.nprow, self.npcol, self.order, self.rsrc, self.csrc = nprow, npcol, order, rsrc, csrc
+        self.lld_pad = lld_pad
+
+    def coords(self, rank):
+        if self.order == "C":
+            return rank % self.nprow, rank // self.nprow
+        return rank // self.npcol, rank % self.npcol
+
+    def local_shape(self, rank):
+        pr, pc = self.coords(rank)
+        lr = costa.numroc(self.M, self.mb, pr, self.rsrc, self.nprow)
+        lc = costa.numroc(self.N, self.nb, pc, self.csrc, self.npcol)
+        return max(lr, 1) + self.lld_pad, lc  # (lld, local columns)
+
+    def desc(self, rank):
+        return costa.descinit(self.M, self.N, self.mb, self.nb, self.rsrc, self.csrc, self.local_shape(rank)[0])
+
+    def _blocks(self, rank):
+        lld = self.local_shape(rank)[0]
+        rs, cs, _, blocks = costa.scalapack_grid(lld, self.M, self.N, 1, 1, self.M, self.N, self.mb, self.nb, self.nprow, self.npcol, self.order,
+                                                 self.rsrc, self.csrc, "C", rank)
+        return lld, rs, cs, blocks
+
+    def scatter(self, G, rank, fill=0):
+        """-> the rank's local array (1-D, lld * local columns) holding its part of G."""
+        lld, lc = self.local_shape(rank)
+        loc = np.full(max(lld * lc, 1), fill, dtype=G.dtype)
+        if rank >= self.nprow * self.npcol:
+            return loc
+        lld, rs, cs, blocks = self._blocks(rank)
+        L = loc[:lld * lc].reshape(lc, lld).T if lc else None
+        for (bi, bj, off) in blocks:
+            r0, c0 = off % lld, off // lld
+            L[r0:r0 + rs[bi + 1] - rs[bi], c0:c0 + cs[bj + 1] - cs[bj]] = G[rs[bi]:rs[bi + 1], cs[bj]:cs[bj + 1]]
+        return loc
+
+    def gather_into(self, G, loc, rank):
+        if rank >= self.nprow * self.npcol:
+            return
+        lld, lc = self.local_shape(rank)
+        lld, rs, cs, blocks = self._blocks(rank)
+        L = loc[:lld * lc].reshape(lc, lld).T if lc else None
+        for (bi, bj, off) in blocks:
+            r0, c0 = off % lld, off // lld
+            G[rs[bi]:rs[bi + 1], cs[bj]:cs[bj + 1]] = L[r0:r0 + rs[bi + 1] - rs[bi], c0:c0 + cs[bj + 1] - cs[bj]]
