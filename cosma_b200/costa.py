@@ -58,6 +58,7 @@ def _declare(lib):
     lib.cosma_b200_grid_info.argtypes = [vp, pi, pi, pi, pi]
     for name in ("cosma_b200_pdgemm", "cosma_b200_pzgemm"):
         getattr(lib, name).argtypes = [vp, ctypes.c_char, ctypes.c_char, ci, ci, ci, pd, vp, ci, ci, pi, vp, ci, ci, pi, pd, vp, ci, ci, pi, vp]
+    lib.cosma_b200_last_layout_multiply_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i64), cp, ci, pi]
     lib._costa_declared = True
 
 
@@ -254,3 +255,15 @@ def pxgemm(grid, dtype, transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib,
     da, db, dc = (np.ascontiguousarray(d, dtype=np.int32) for d in (desca, descb, descc))
     _lib.check(fn(grid.handle, transa.encode(), transb.encode(), m, n, k, al, vp(a), ia, ja, da.ctypes.data_as(pi), vp(b), ib, jb,
                   db.ctypes.data_as(pi), be, vp(c), ic, jc, dc.ctypes.data_as(pi), _stream_ptr(stream)), "cosma_b200_p%sgemm" % dtype)
+
+
+def last_layout_multiply_stats(comm):
+    """Phase timings (ms) and relayout volumes of the last multiply_using_layout / pxgemm on comm (synchronise first)."""
+    L = lib()
+    ms = (ctypes.c_float * 3)()
+    el = (i64 * 4)()
+    buf = ctypes.create_string_buffer(256)
+    n = ci()
+    _lib.check(L.cosma_b200_last_layout_multiply_stats(comm.handle, ms, el, buf, 256, ctypes.byref(n)), "cosma_b200_last_layout_multiply_stats")
+    return {"ms_relayout_in": ms[0], "ms_multiply": ms[1], "ms_relayout_out": ms[2], "in_local_elements": el[0], "in_remote_elements": el[1],
+            "out_local_elements": el[2], "out_remote_elements": el[3], "strategy": buf.value.decode(), "launches": n.value}

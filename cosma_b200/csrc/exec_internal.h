@@ -23,6 +23,7 @@ struct Comm {
     // state cached across ?multiply_using_layout / p?gemm calls on this communicator (the reference caches the
     // communicator + strategy in its context, context.cpp:80-125); destroyed with the communicator
     std::map<std::string, LayoutMultiplyState*> layout_states;
+    LayoutMultiplyState* last_layout_state = nullptr;
     ~Comm();
 };
 

@@ -32,8 +32,12 @@ struct LayoutMultiplyState {
     std::vector<Entry> transforms;  // small LRU of transform plans keyed by the caller's layouts
     std::uint64_t clock = 0;
     int last_launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start | A,B relayouted | multiplied | C relayouted
+    std::int64_t last_elements[4] = {0, 0, 0, 0};              // in: local, remote; out: local, remote
     ~LayoutMultiplyState() {
         transforms.clear();
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
         for (auto& a : arena)
             if (a) cudaFree(a);
         if (plan) cosma_b200_plan_destroy(plan);
@@ -212,14 +216,25 @@ int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, 
         entry = &st->transforms.back();
     }
     entry->stamp = ++st->clock;
+    for (auto& e : st->ev)
+        if (!e) COSMA_B200_CUDA_TRY(cudaEventCreate(&e));
+    c->last_layout_state = st;
+    st->last_elements[0] = entry->in->host.local_elements;
+    st->last_elements[1] = entry->in->host.remote_elements;
+    st->last_elements[2] = entry->out->host.local_elements;
+    st->last_elements[3] = entry->out->host.remote_elements;
 
+    COSMA_B200_CUDA_TRY(cudaEventRecord(st->ev[0], stream));
     rc = transform_plan_run(*entry->in, stream);
     if (rc != COSMA_B200_OK) return rc;
+    COSMA_B200_CUDA_TRY(cudaEventRecord(st->ev[1], stream));
     const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
     rc = cosma_b200_multiply(st->plan, one, zero, st->arena[0], st->arena[1], st->arena[2], stream);
     if (rc != COSMA_B200_OK) return rc;
+    COSMA_B200_CUDA_TRY(cudaEventRecord(st->ev[2], stream));
     rc = transform_plan_run(*entry->out, stream);
     if (rc != COSMA_B200_OK) return rc;
+    COSMA_B200_CUDA_TRY(cudaEventRecord(st->ev[3], stream));
     st->last_launches = entry->in->last_launches + entry->out->last_launches + cosma_b200_plan_last_launches(st->plan);
     if (launches) *launches = st->last_launches;
     return COSMA_B200_OK;
@@ -270,6 +285,19 @@ int cosma_b200_zmultiply_using_layout(void* comm, const char* transa, const char
                                       const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
                                       const cosma_b200_layout* C, void* stream) {
     return xmultiply_using_layout(comm, 'z', transa, transb, alpha, A, B, beta, C, stream);
+}
+
+int cosma_b200_last_layout_multiply_stats(void* comm, float* ms3, int64_t* elements4, char* strategy, int strategy_len, int* launches) {
+    Comm* c = static_cast<Comm*>(comm);
+    if (!c || !c->last_layout_state) return COSMA_B200_INVALID_ARG;
+    LayoutMultiplyState* st = c->last_layout_state;
+    if (ms3)
+        for (int i = 0; i < 3; ++i)
+            if (cudaEventElapsedTime(&ms3[i], st->ev[i], st->ev[i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+    if (elements4) std::memcpy(elements4, st->last_elements, sizeof(st->last_elements));
+    if (strategy) cosma_b200_plan_strategy(st->plan, strategy, strategy_len, nullptr);
+    if (launches) *launches = st->last_launches;
+    return COSMA_B200_OK;
 }
 
 int cosma_b200_grid_create(void* comm, char order, int nprow, int npcol, void** grid_out) {

@@ -189,6 +189,12 @@ COSMA_B200_API int cosma_b200_zmultiply_using_layout(void* comm, const char* tra
                                                      const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
                                                      const cosma_b200_layout* C, void* stream);
 
+/* After a synchronised ?multiply_using_layout / p?gemm on `comm`: device milliseconds of its three phases (relayout
+ * of A and B in, multiply, relayout of C out), elements moved by this rank's relayouts (in: staying on the rank, sent to
+ * peers; out: same), the strategy used ("pm2,pn2,pk2") and the number of kernels launched. */
+COSMA_B200_API int cosma_b200_last_layout_multiply_stats(void* comm, float* ms3, int64_t* elements4, char* strategy, int strategy_len,
+                                                         int* launches);
+
 /* ---- ScaLAPACK p?gemm ------------------------------------------------------------------------------------
  * Process grid = what BLACS answers for the context id in desc[1] (Cblacs_gridinfo / Cblacs_get; reference
  * src/cosma/blacs.hpp:5-35, scalapack.cpp:3-46, cosma_pxgemm.cpp:57-69). BLACS does not exist on this box, so the grid
