@@ -51,12 +51,12 @@ def _declare(lib):
     lib.cosma_b200_scalapack_layout.argtypes = [ci] * 11 + [ctypes.c_char, ci, ci, ctypes.c_char, ci, pi, pi, pi, pi, pi, pi, pi, pi,
                                                 ctypes.POINTER(i64)]
     lib.cosma_b200_numroc.argtypes = [ci] * 5
-    for name in ("cosma_b200_dmultiply_using_layout", "cosma_b200_zmultiply_using_layout"):
+    for name in ("cosma_b200_%smultiply_using_layout" % t for t in "sdcz"):
         getattr(lib, name).argtypes = [vp, cp, cp, pd, ctypes.POINTER(CLayout), ctypes.POINTER(CLayout), pd, ctypes.POINTER(CLayout), vp]
     lib.cosma_b200_grid_create.argtypes = [vp, ctypes.c_char, ci, ci, ctypes.POINTER(vp)]
     lib.cosma_b200_grid_destroy.argtypes = [vp]
     lib.cosma_b200_grid_info.argtypes = [vp, pi, pi, pi, pi]
-    for name in ("cosma_b200_pdgemm", "cosma_b200_pzgemm"):
+    for name in ("cosma_b200_p%sgemm" % t for t in "sdcz"):
         getattr(lib, name).argtypes = [vp, ctypes.c_char, ctypes.c_char, ci, ci, ci, pd, vp, ci, ci, pi, vp, ci, ci, pi, pd, vp, ci, ci, pi, vp]
     lib.cosma_b200_last_layout_multiply_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i64), cp, ci, pi]
     lib._costa_declared = True
@@ -217,7 +217,7 @@ def relayout_batch(dtype, pieces, stream=None):
 def multiply_using_layout(comm, dtype, transa, transb, alpha, A, B, beta, C, stream=None):
     """{d,z}multiply_using_layout (reference src/cosma/cinterface.hpp:42-76). A, B, C: Layout with device blocks."""
     L = lib()
-    fn = {"d": L.cosma_b200_dmultiply_using_layout, "z": L.cosma_b200_zmultiply_using_layout}[dtype]
+    fn = getattr(L, "cosma_b200_%smultiply_using_layout" % dtype)
     al, be = _scalars([alpha], dtype, 1), _scalars([beta], dtype, 1)
     a, b, c = A.c_struct(), B.c_struct(), C.c_struct()
     _lib.check(fn(comm.handle, transa.encode(), transb.encode(), al, ctypes.byref(a), ctypes.byref(b), be, ctypes.byref(c), _stream_ptr(stream)),
@@ -250,7 +250,7 @@ def descinit(m, n, mb, nb, rsrc, csrc, lld, ctxt=0):
 def pxgemm(grid, dtype, transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib, jb, descb, beta, c, ic, jc, descc, stream=None):
     """p{d,z}gemm (reference src/cosma/pxgemm.h:6-107). a, b, c: addresses of the rank's local arrays (device or host)."""
     L = lib()
-    fn = {"d": L.cosma_b200_pdgemm, "z": L.cosma_b200_pzgemm}[dtype]
+    fn = getattr(L, "cosma_b200_p%sgemm" % dtype)
     al, be = _scalars([alpha], dtype, 1), _scalars([beta], dtype, 1)
     da, db, dc = (np.ascontiguousarray(d, dtype=np.int32) for d in (desca, descb, descc))
     _lib.check(fn(grid.handle, transa.encode(), transb.encode(), m, n, k, al, vp(a), ia, ja, da.ctypes.data_as(pi), vp(b), ib, jb,

@@ -1,6 +1,7 @@
 // extern "C" surface of libcosma_b200.so (declared in include/cosma_b200.h).
 #include "../../include/cosma_b200.h"
 #include "gemm_f64_sm100.h"
+#include "gemm_tf32x3_sm100.h"
 
 #include <string>
 
@@ -34,6 +35,20 @@ int cosma_b200_zgemm(void* stream, char transa, char transb, int64_t m, int64_t 
     if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
     return cosma_b200::zgemm_sm100(static_cast<cudaStream_t>(stream), transa, transb, m, n, k, alpha, A, lda, B, ldb, beta,
                                    C, ldc, &g_last_gemm_path);
+}
+
+int cosma_b200_sgemm(void* stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const float* alpha, const float* A,
+                     int64_t lda, const float* B, int64_t ldb, const float* beta, float* C, int64_t ldc) {
+    if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
+    return cosma_b200::sgemm_sm100(static_cast<cudaStream_t>(stream), transa, transb, m, n, k, *alpha, A, lda, B, ldb, *beta, C, ldc,
+                                   &g_last_gemm_path);
+}
+
+int cosma_b200_cgemm(void* stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const float* alpha, const float* A,
+                     int64_t lda, const float* B, int64_t ldb, const float* beta, float* C, int64_t ldc) {
+    if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
+    return cosma_b200::cgemm_sm100(static_cast<cudaStream_t>(stream), transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
+                                   &g_last_gemm_path);
 }
 
 int cosma_b200_dgemm_host(void* stream, int64_t m, int64_t n, int64_t k, const double* alpha, const double* A, int64_t lda,

@@ -30,17 +30,19 @@ struct Comm {
 struct Plan {
     cosma::Schedule schedule;
     char dtype = 'd';
-    int elem_doubles = 1;  // doubles per element: 1 (d) or 2 (z)
+    int elem_reals = 1;    // real scalars per element: 1 (s, d) or 2 (c, z)
+    int real_bytes = 8;    // 4 (s, c) or 8 (d, z)
+    int elem_bytes() const { return elem_reals * real_bytes; }
     std::vector<ncclComm_t> ring_comms;  // by Schedule::rings() index
     int last_launches = 0;
     std::vector<float> gemm_ms;  // optional per-GEMM timing of the last run
     std::vector<cudaEvent_t> ev;
     bool time_gemms = false;
     // library-owned device arenas for the host-pointer entry point (allocated on first use)
-    double* owned[3] = {nullptr, nullptr, nullptr};
+    char* owned[3] = {nullptr, nullptr, nullptr};
 };
 
-int plan_run(Plan& plan, const double* alpha, const double* beta, double* A, double* B, double* C, cudaStream_t stream);
+int plan_run(Plan& plan, const double* alpha, const double* beta, void* A, void* B, void* C, cudaStream_t stream);
 
 // costa::transform on the device: pack kernel -> grouped ncclSend/ncclRecv -> unpack kernel
 struct TransformPlan {

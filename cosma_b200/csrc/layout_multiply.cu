@@ -173,10 +173,6 @@ int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, 
     // corner cases allowed by the BLAS standard (multiply.cpp:96-109, cosma_pxgemm.cpp:36-46)
     if (m == 0 || n == 0) return COSMA_B200_OK;
     if (k == 0 || is_zero(alpha, cplx)) return scale_layout(dtype, C, beta, stream);
-    if (dtype != 'd' && dtype != 'z') {
-        set_last_error("multiply_using_layout: only 'd' and 'z' have a GEMM kernel in this build");
-        return COSMA_B200_NOT_SUPPORTED;
-    }
     LayoutMultiplyState* st = nullptr;
     int rc = get_state(c, dtype, m, n, k, steps, &st);
     if (rc != COSMA_B200_OK) return rc;
@@ -300,6 +296,17 @@ int cosma_b200_last_layout_multiply_stats(void* comm, float* ms3, int64_t* eleme
     return COSMA_B200_OK;
 }
 
+int cosma_b200_smultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
+                                      const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                      const cosma_b200_layout* C, void* stream) {
+    return xmultiply_using_layout(comm, 's', transa, transb, alpha, A, B, beta, C, stream);
+}
+int cosma_b200_cmultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
+                                      const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                      const cosma_b200_layout* C, void* stream) {
+    return xmultiply_using_layout(comm, 'c', transa, transb, alpha, A, B, beta, C, stream);
+}
+
 int cosma_b200_grid_create(void* comm, char order, int nprow, int npcol, void** grid_out) {
     Comm* c = static_cast<Comm*>(comm);
     if (!c || !grid_out || nprow < 1 || npcol < 1 || nprow * npcol > c->size) {
@@ -416,6 +423,17 @@ int cosma_b200_pzgemm(void* grid, char transa, char transb, int m, int n, int k,
                       const int* desca, const double* b, int ib, int jb, const int* descb, const double* beta, double* c, int ic, int jc,
                       const int* descc, void* stream) {
     return xpgemm(grid, 'z', transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib, jb, descb, beta, c, ic, jc, descc, stream);
+}
+
+int cosma_b200_psgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const float* a, int ia, int ja,
+                      const int* desca, const float* b, int ib, int jb, const int* descb, const double* beta, float* c, int ic, int jc,
+                      const int* descc, void* stream) {
+    return xpgemm(grid, 's', transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib, jb, descb, beta, c, ic, jc, descc, stream);
+}
+int cosma_b200_pcgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const float* a, int ia, int ja,
+                      const int* desca, const float* b, int ib, int jb, const int* descb, const double* beta, float* c, int ic, int jc,
+                      const int* descc, void* stream) {
+    return xpgemm(grid, 'c', transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib, jb, descb, beta, c, ic, jc, descc, stream);
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 // DGEMM/ZGEMM kernels. Operands never leave HBM.
 #include "exec_internal.h"
 #include "gemm_f64_sm100.h"
+#include "gemm_tf32x3_sm100.h"
 
 #include <cstring>
 
@@ -13,29 +14,14 @@ namespace cosma_b200 {
 namespace {
 
 // C[i] = beta * C[i] + T[i]  (E1: the reference's host loop, two_sided_communicator.cpp:219-224)
-template <bool CPLX>
-__global__ void axpby_kernel(int64_t n, double br, double bi, double* __restrict__ C, const double* __restrict__ T) {
+template <typename R, bool CPLX>
+__global__ void axpby_kernel(int64_t n, R br, R bi, R* __restrict__ C, const R* __restrict__ T) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     if (!CPLX) {
-        const int64_t n2 = n / 2;
-        const bool vec = ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(T)) & 15) == 0;
-        if (vec) {
-            double2* c2 = reinterpret_cast<double2*>(C);
-            const double2* t2 = reinterpret_cast<const double2*>(T);
-            for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n2; i += stride) {
-                double2 c = c2[i];
-                const double2 t = t2[i];
-                c.x = br * c.x + t.x;
-                c.y = br * c.y + t.y;
-                c2[i] = c;
-            }
-            if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) C[n - 1] = br * C[n - 1] + T[n - 1];
-        } else {
-            for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += stride) C[i] = br * C[i] + T[i];
-        }
+        for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += stride) C[i] = br * C[i] + T[i];
     } else {
         for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += stride) {
-            const double cr = C[2 * i], ci = C[2 * i + 1];
+            const R cr = C[2 * i], ci = C[2 * i + 1];
             C[2 * i] = br * cr - bi * ci + T[2 * i];
             C[2 * i + 1] = br * ci + bi * cr + T[2 * i + 1];
         }
@@ -45,16 +31,18 @@ __global__ void axpby_kernel(int64_t n, double br, double bi, double* __restrict
 #define NCCL_TRY COSMA_B200_NCCL_TRY
 #define CUDA_TRY COSMA_B200_CUDA_TRY
 
-int run_allgather(const Plan& plan, const cosma::ScheduleOp& op, double* arena, cudaStream_t stream) {
+int run_allgather(const Plan& plan, const cosma::ScheduleOp& op, char* arena, cudaStream_t stream) {
     const NcclApi* N = nccl();
-    const int E = plan.elem_doubles;
+    const int E = plan.elem_reals;                 // NCCL counts are in real scalars (complex = 2 x real, nccl_utils.cpp:105-107)
+    const int64_t EB = plan.elem_bytes();
+    const ncclDataType_t ndt = plan.real_bytes == 8 ? ncclDouble : ncclFloat;
     ncclComm_t comm = plan.ring_comms[op.ring_index];
     const int div = static_cast<int>(op.ring.size());
     const size_t nb = op.piece[0].size();
-    const double* src = arena + op.src_off * E;
-    double* dst = arena + op.dst_off * E;
+    const char* src = arena + op.src_off * EB;
+    char* dst = arena + op.dst_off * EB;
     if (op.regular) {
-        NCCL_TRY(N->AllGather(src, dst, static_cast<size_t>(op.piece[0][0]) * E, ncclDouble, comm, stream));
+        NCCL_TRY(N->AllGather(src, dst, static_cast<size_t>(op.piece[0][0]) * E, ndt, comm, stream));
         return COSMA_B200_OK;
     }
     // exact placement: bucket-major destination, member-major inside a bucket
@@ -66,10 +54,9 @@ int run_allgather(const Plan& plan, const cosma::ScheduleOp& op, double* arena, 
             const int64_t cnt = op.piece[g][b];
             if (cnt > 0) {
                 if (g == op.my_pos) {
-                    CUDA_TRY(cudaMemcpyAsync(dst + dst_off * E, src + src_off[g] * E, cnt * E * sizeof(double),
-                                             cudaMemcpyDeviceToDevice, stream));
+                    CUDA_TRY(cudaMemcpyAsync(dst + dst_off * EB, src + src_off[g] * EB, cnt * EB, cudaMemcpyDeviceToDevice, stream));
                 } else {
-                    NCCL_TRY(N->Recv(dst + dst_off * E, static_cast<size_t>(cnt) * E, ncclDouble, g, comm, stream));
+                    NCCL_TRY(N->Recv(dst + dst_off * EB, static_cast<size_t>(cnt) * E, ndt, g, comm, stream));
                 }
             }
             src_off[g] += cnt;
@@ -80,15 +67,17 @@ int run_allgather(const Plan& plan, const cosma::ScheduleOp& op, double* arena, 
         if (mine > 0)
             for (int g = 0; g < div; ++g)
                 if (g != op.my_pos)
-                    NCCL_TRY(N->Send(src + (src_off[op.my_pos] - mine) * E, static_cast<size_t>(mine) * E, ncclDouble, g, comm, stream));
+                    NCCL_TRY(N->Send(src + (src_off[op.my_pos] - mine) * EB, static_cast<size_t>(mine) * E, ndt, g, comm, stream));
     }
     NCCL_TRY(N->GroupEnd());
     return COSMA_B200_OK;
 }
 
-int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, double* arena, const double* beta_user, cudaStream_t stream) {
+int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, char* arena, const double* beta_user, cudaStream_t stream) {
     const NcclApi* N = nccl();
-    const int E = plan.elem_doubles;
+    const int E = plan.elem_reals;
+    const int64_t EB = plan.elem_bytes();
+    const ncclDataType_t ndt = plan.real_bytes == 8 ? ncclDouble : ncclFloat;
     ncclComm_t comm = plan.ring_comms[op.ring_index];
     const int div = static_cast<int>(op.ring.size());
     const size_t nb = op.piece[0].size();
@@ -96,13 +85,13 @@ int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, double* arena, con
     if (op.beta == cosma::BetaMode::ONE) br = 1.0;
     else if (op.beta == cosma::BetaMode::USER) { br = beta_user[0]; bi = E == 2 ? beta_user[1] : 0.0; }
     const bool beta_zero = br == 0.0 && bi == 0.0;
-    const double* src = arena + op.src_off * E;
-    double* dst = arena + op.dst_off * E;
-    double* recv = beta_zero ? dst : arena + op.tmp_off * E;
+    const char* src = arena + op.src_off * EB;
+    char* dst = arena + op.dst_off * EB;
+    char* recv = beta_zero ? dst : arena + op.tmp_off * EB;
     int64_t mine_total = 0;
     for (auto v : op.piece[op.my_pos]) mine_total += v;
     if (op.regular) {
-        NCCL_TRY(N->ReduceScatter(src, recv, static_cast<size_t>(op.piece[0][0]) * E, ncclDouble, ncclSum, comm, stream));
+        NCCL_TRY(N->ReduceScatter(src, recv, static_cast<size_t>(op.piece[0][0]) * E, ndt, ncclSum, comm, stream));
     } else {
         // reduce-scatter-v with exact counts: one rooted reduction per (bucket, member), fused in one NCCL group
         int64_t off = 0, roff = 0;
@@ -111,8 +100,8 @@ int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, double* arena, con
             for (int g = 0; g < div; ++g) {
                 const int64_t cnt = op.piece[g][b];
                 if (cnt > 0)
-                    NCCL_TRY(N->Reduce(src + off * E, g == op.my_pos ? recv + roff * E : nullptr, static_cast<size_t>(cnt) * E,
-                                       ncclDouble, ncclSum, g, comm, stream));
+                    NCCL_TRY(N->Reduce(src + off * EB, g == op.my_pos ? recv + roff * EB : nullptr, static_cast<size_t>(cnt) * E, ndt, ncclSum,
+                                       g, comm, stream));
                 if (g == op.my_pos) roff += cnt;
                 off += cnt;
             }
@@ -120,11 +109,17 @@ int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, double* arena, con
     }
     if (!beta_zero && mine_total > 0) {
         const int threads = 256;
-        const int64_t work = E == 2 ? mine_total : (mine_total + 1) / 2;
-        int blocks = static_cast<int>(std::min<int64_t>((work + threads - 1) / threads, 148 * 8));
+        int blocks = static_cast<int>(std::min<int64_t>((mine_total + threads - 1) / threads, 148 * 8));
         if (blocks < 1) blocks = 1;
-        if (E == 1) axpby_kernel<false><<<blocks, threads, 0, stream>>>(mine_total, br, bi, dst, recv);
-        else axpby_kernel<true><<<blocks, threads, 0, stream>>>(mine_total, br, bi, dst, recv);
+        const int64_t cnt = E == 2 ? mine_total : mine_total;
+        if (plan.real_bytes == 8) {
+            if (E == 1) axpby_kernel<double, false><<<blocks, threads, 0, stream>>>(cnt, br, bi, reinterpret_cast<double*>(dst), reinterpret_cast<const double*>(recv));
+            else axpby_kernel<double, true><<<blocks, threads, 0, stream>>>(cnt, br, bi, reinterpret_cast<double*>(dst), reinterpret_cast<const double*>(recv));
+        } else {
+            const float fr = static_cast<float>(br), fi = static_cast<float>(bi);
+            if (E == 1) axpby_kernel<float, false><<<blocks, threads, 0, stream>>>(cnt, fr, fi, reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(recv));
+            else axpby_kernel<float, true><<<blocks, threads, 0, stream>>>(cnt, fr, fi, reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(recv));
+        }
         CUDA_TRY(cudaGetLastError());
     }
     return COSMA_B200_OK;
@@ -132,9 +127,13 @@ int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, double* arena, con
 
 }  // namespace
 
-int plan_run(Plan& plan, const double* alpha, const double* beta, double* A, double* B, double* C, cudaStream_t stream) {
-    const int E = plan.elem_doubles;
-    double* arenas[3] = {A, B, C};
+int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void* B_, void* C_, cudaStream_t stream) {
+    const int E = plan.elem_reals;
+    const int64_t EB = plan.elem_bytes();
+    char* A = static_cast<char*>(A_);
+    char* B = static_cast<char*>(B_);
+    char* C = static_cast<char*>(C_);
+    char* arenas[3] = {A, B, C};
     plan.last_launches = 0;
     size_t n_gemm = 0;
     for (const auto& op : plan.schedule.ops()) n_gemm += op.kind == cosma::OpKind::GEMM;
@@ -145,6 +144,7 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, double* A, dou
             plan.ev.push_back(e);
         }
     }
+    const float alpha_f[2] = {static_cast<float>(alpha[0]), E == 2 ? static_cast<float>(alpha[1]) : 0.0f};
     size_t gi = 0;
     for (const auto& op : plan.schedule.ops()) {
         int st = COSMA_B200_OK;
@@ -153,14 +153,31 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, double* A, dou
                 double b[2] = {0.0, 0.0};
                 if (op.beta == cosma::BetaMode::ONE) b[0] = 1.0;
                 else if (op.beta == cosma::BetaMode::USER) { b[0] = beta[0]; b[1] = E == 2 ? beta[1] : 0.0; }
+                const float b_f[2] = {static_cast<float>(b[0]), static_cast<float>(b[1])};
                 int path = 0;
                 if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * gi], stream));
-                if (E == 1)
-                    st = dgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha[0], A + op.a_off, std::max(op.m, 1), B + op.b_off,
-                                     std::max(op.k, 1), b[0], C + op.c_off, std::max(op.m, 1), &path);
-                else
-                    st = zgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha, A + 2 * op.a_off, std::max(op.m, 1),
-                                     B + 2 * op.b_off, std::max(op.k, 1), b, C + 2 * op.c_off, std::max(op.m, 1), &path);
+                const int64_t lda = std::max(op.m, 1), ldb = std::max(op.k, 1), ldc = std::max(op.m, 1);
+                void* a = A + op.a_off * EB;
+                void* bp = B + op.b_off * EB;
+                void* c = C + op.c_off * EB;
+                switch (plan.dtype) {
+                    case 'd':
+                        st = dgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha[0], static_cast<double*>(a), lda, static_cast<double*>(bp), ldb, b[0],
+                                         static_cast<double*>(c), ldc, &path);
+                        break;
+                    case 'z':
+                        st = zgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha, static_cast<double*>(a), lda, static_cast<double*>(bp), ldb, b,
+                                         static_cast<double*>(c), ldc, &path);
+                        break;
+                    case 's':
+                        st = sgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha_f[0], static_cast<float*>(a), lda, static_cast<float*>(bp), ldb, b_f[0],
+                                         static_cast<float*>(c), ldc, &path);
+                        break;
+                    default:
+                        st = cgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha_f, static_cast<float*>(a), lda, static_cast<float*>(bp), ldb, b_f,
+                                         static_cast<float*>(c), ldc, &path);
+                        break;
+                }
                 if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * gi + 1], stream));
                 ++gi;
                 if (path) ++plan.last_launches;
@@ -230,9 +247,9 @@ int cosma_b200_comm_destroy(void* comm) {
 int cosma_b200_plan_create(void* comm, int rank, int nranks, int m, int n, int k, const char* steps, char dtype,
                            void** plan_out) {
     try {
-        if (dtype != 'd' && dtype != 'z') {
-            set_last_error("plan dtype must be 'd' or 'z'");
-            return COSMA_B200_NOT_SUPPORTED;
+        if (dtype != 'd' && dtype != 'z' && dtype != 's' && dtype != 'c') {
+            set_last_error("plan dtype must be one of s, d, c, z");
+            return COSMA_B200_INVALID_ARG;
         }
         Comm* c = static_cast<Comm*>(comm);
         if (c) { rank = c->rank; nranks = c->size; }
@@ -240,7 +257,8 @@ int cosma_b200_plan_create(void* comm, int rank, int nranks, int m, int n, int k
         auto plan = std::make_unique<Plan>();
         plan->schedule = cosma::Schedule(strategy, rank);
         plan->dtype = dtype;
-        plan->elem_doubles = dtype == 'z' ? 2 : 1;
+        plan->elem_reals = (dtype == 'z' || dtype == 'c') ? 2 : 1;
+        plan->real_bytes = (dtype == 'd' || dtype == 'z') ? 8 : 4;
         if (c && nranks > 1) {
             const auto* N = nccl();
             // one communicator split per parallel step, called by EVERY rank of the parent communicator in step
@@ -299,7 +317,7 @@ int cosma_b200_plan_strategy(void* plan, char* out, int out_len, int* P_used) {
 }
 double cosma_b200_plan_gemm_flops(void* plan) {
     Plan* p = static_cast<Plan*>(plan);
-    return p->schedule.total_gemm_flops() * (p->elem_doubles == 2 ? 4.0 : 1.0);
+    return p->schedule.total_gemm_flops() * (p->elem_reals == 2 ? 4.0 : 1.0);
 }
 int cosma_b200_plan_export(void* plan, int64_t* buf, int64_t cap, int64_t* len) {
     const auto v = static_cast<Plan*>(plan)->schedule.serialize();
@@ -328,8 +346,7 @@ int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, voi
         set_last_error("plan was created without a communicator (plan-only); cannot execute collectives");
         return COSMA_B200_INVALID_ARG;
     }
-    return cosma_b200::plan_run(*p, alpha, beta, static_cast<double*>(A), static_cast<double*>(B), static_cast<double*>(C),
-                                static_cast<cudaStream_t>(stream));
+    return cosma_b200::plan_run(*p, alpha, beta, A, B, C, static_cast<cudaStream_t>(stream));
 }
 
 /* Host-pointer variant: local A, B (and C when beta != 0) are uploaded from (pinned) host memory into arenas owned by
@@ -342,7 +359,7 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
     if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
     if (p->schedule.idle()) return COSMA_B200_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t es = sizeof(double) * p->elem_doubles;
+    const size_t es = static_cast<size_t>(p->elem_bytes());
     for (int x = 0; x < 3; ++x)
         if (!p->owned[x]) {
             const size_t bytes = std::max<size_t>(p->schedule.arena_elements(x), 1) * es;
@@ -351,7 +368,7 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
                 return COSMA_B200_OUT_OF_MEMORY;
             }
         }
-    const bool beta_zero = beta[0] == 0.0 && (p->elem_doubles == 1 || beta[1] == 0.0);
+    const bool beta_zero = beta[0] == 0.0 && (p->elem_reals == 1 || beta[1] == 0.0);
     const void* host_in[3] = {A, B, C};
     for (int x = 0; x < 3; ++x) {
         if (x == 2 && beta_zero) continue;

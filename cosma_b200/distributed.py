@@ -130,7 +130,7 @@ class MultiplyPlan:
         self.A = self.B = self.C = None
         if allocate:
             import torch
-            tdt = {"d": torch.float64, "z": torch.complex128}[dtype]
+            tdt = {"d": torch.float64, "z": torch.complex128, "s": torch.float32, "c": torch.complex64}[dtype]
             dev = device or torch.device("cuda", torch.cuda.current_device())
             mats = []
             for x, label in enumerate("ABC"):
@@ -158,7 +158,7 @@ class MultiplyPlan:
 
     def multiply(self, alpha=1.0, beta=0.0, stream=None):
         import torch
-        if self.dtype == "d":
+        if self.dtype in "ds":
             al = (ctypes.c_double * 1)(float(alpha)); be = (ctypes.c_double * 1)(float(beta))
         else:
             al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
@@ -173,7 +173,7 @@ class MultiplyPlan:
     def multiply_host(self, hA, hB, hC, alpha=1.0, beta=0.0, stream=None):
         """hA, hB, hC: pinned host tensors holding the rank's local matrices (reference layout)."""
         import torch
-        if self.dtype == "d":
+        if self.dtype in "ds":
             al = (ctypes.c_double * 1)(float(alpha)); be = (ctypes.c_double * 1)(float(beta))
         else:
             al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)

@@ -17,18 +17,24 @@ def _stream_ptr(stream):
 
 
 def gemm_raw(dtype, transa, transb, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc, stream=None):
-    """dtype: 'd' or 'z'. a_ptr/b_ptr/c_ptr: device addresses (int). alpha/beta: python float or complex."""
+    """dtype: 'd' | 'z' (FP64 DMMA kernels) or 's' | 'c' (3xTF32 tcgen05 kernels). a_ptr/b_ptr/c_ptr: device addresses
+    (int). alpha/beta: python float or complex."""
     lib = _lib.load()
-    if dtype == "d":
-        al = (ctypes.c_double * 1)(float(alpha))
-        be = (ctypes.c_double * 1)(float(beta))
-        fn = lib.cosma_b200_dgemm
-    elif dtype == "z":
-        al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
-        be = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
-        fn = lib.cosma_b200_zgemm
+    ctype = ctypes.c_double if dtype in "dz" else ctypes.c_float
+    if dtype in "ds":
+        al = (ctype * 1)(float(alpha))
+        be = (ctype * 1)(float(beta))
+    elif dtype in "zc":
+        al = (ctype * 2)(complex(alpha).real, complex(alpha).imag)
+        be = (ctype * 2)(complex(beta).real, complex(beta).imag)
     else:
         raise ValueError(dtype)
+    fn = getattr(lib, "cosma_b200_%sgemm" % dtype)
+    if dtype in "sc" and not getattr(fn, "_declared", False):
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_char, ctypes.c_char, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_float),
+                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_float), ctypes.c_void_p, ctypes.c_int64]
+        fn.restype = ctypes.c_int
+        fn._declared = True
     st = fn(_stream_ptr(stream), transa.encode(), transb.encode(), m, n, k, al, ctypes.c_void_p(a_ptr), lda,
             ctypes.c_void_p(b_ptr), ldb, be, ctypes.c_void_p(c_ptr), ldc)
     _lib.check(st, "cosma_b200_%sgemm" % dtype)
@@ -37,6 +43,6 @@ def gemm_raw(dtype, transa, transb, m, n, k, alpha, a_ptr, lda, b_ptr, ldb, beta
 def local_multiply(A, B, C, m, n, k, alpha, beta, stream=None):
     """A, B, C: 1-D torch CUDA tensors holding column-major m x k, k x n, m x n (lda=m, ldb=k, ldc=m)."""
     import torch
-    dt = {torch.float64: "d", torch.complex128: "z"}[C.dtype]
+    dt = {torch.float64: "d", torch.complex128: "z", torch.float32: "s", torch.complex64: "c"}[C.dtype]
     gemm_raw(dt, "N", "N", m, n, k, alpha, A.data_ptr(), max(m, 1), B.data_ptr(), max(k, 1), beta, C.data_ptr(),
              max(m, 1), stream)

@@ -50,7 +50,17 @@ COSMA_B200_API int cosma_b200_dgemm(void* stream, char transa, char transb, int6
 COSMA_B200_API int cosma_b200_zgemm(void* stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const double* alpha,
                      const double* A, int64_t lda, const double* B, int64_t ldb, const double* beta, double* C,
                      int64_t ldc);
-/* Which kernel the last ?gemm call on this thread used: 0 none, 1 TMA+DMMA persistent, 2 generic. */
+/* K3/K4: single precision on the tcgen05 tensor cores with the 3xTF32 split (FP32 accumulation in TMEM); same contract
+ * as above with float data (cblas_sgemm / cblas_cgemm, cublasSgemm / cublasCgemm in the reference: src/cosma/blas.cpp:
+ * 24-130, libs/Tiled-MM/src/Tiled-MM/tiled_mm.cpp:181-268). Normwise error ~1e-6 or better against an FP32 GEMM.
+ * CGEMM runs on the tensor cores for transa = transb = 'N' (the only form cosma::multiply issues); other complex
+ * transposes use the generic kernel. */
+COSMA_B200_API int cosma_b200_sgemm(void* stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const float* alpha,
+                     const float* A, int64_t lda, const float* B, int64_t ldb, const float* beta, float* C, int64_t ldc);
+COSMA_B200_API int cosma_b200_cgemm(void* stream, char transa, char transb, int64_t m, int64_t n, int64_t k, const float* alpha,
+                     const float* A, int64_t lda, const float* B, int64_t ldb, const float* beta, float* C, int64_t ldc);
+/* Which kernel the last ?gemm call on this thread used: 0 none, 1 TMA + tensor-pipe persistent kernel (DMMA for d/z,
+ * tcgen05 for s/c), 2 generic. */
 COSMA_B200_API int cosma_b200_last_gemm_path(void);
 
 /* ---- planning layer (host only, no CUDA) --------------------------------------------------------
@@ -84,7 +94,7 @@ COSMA_B200_API int cosma_b200_comm_destroy(void* comm);
 /* Plan = Strategy + Mapper x3 + compiled schedule + one ring communicator per parallel step (created collectively:
  * every rank of `comm` must call this with the same m, n, k, steps). comm == NULL builds the plan only (any rank of
  * any nranks; no execution) -- used by tests and tools. steps: "" = automatic (Strategy(m,n,k,P)), else e.g.
- * "pm2,pn2,pk2". dtype: 'd' (double) | 'z' (complex double). */
+ * "pm2,pn2,pk2". dtype: 's' | 'd' | 'c' | 'z' (float, double, complex float, complex double). */
 COSMA_B200_API int cosma_b200_plan_create(void* comm, int rank, int nranks, int m, int n, int k, const char* steps, char dtype,
                                           void** plan_out);
 COSMA_B200_API int cosma_b200_plan_destroy(void* plan);
@@ -98,7 +108,8 @@ COSMA_B200_API double cosma_b200_plan_gemm_flops(void* plan);                  /
 COSMA_B200_API int cosma_b200_plan_export(void* plan, int64_t* buf, int64_t cap, int64_t* len); /* see schedule.cpp */
 COSMA_B200_API int cosma_b200_plan_local_blocks(void* plan, int matrix, int rank, int* out, int cap, int* n_blocks);
 /* C = alpha*A*B + beta*C on the plan's layout. A, B, C: DEVICE arenas of at least plan_arena_elements each; alpha,
- * beta: host pointers (1 double, or 2 for 'z'). Asynchronous on `stream`. Idle ranks return immediately. */
+ * beta: host pointers to doubles for every dtype (1 value, or 2 = (re, im) for 'c'/'z'; converted to float for 's'/'c').
+ * Asynchronous on `stream`. Idle ranks return immediately. */
 COSMA_B200_API int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, void* A, void* B, void* C,
                                        void* stream);
 /* Same with HOST local matrices (pinned for asynchrony): H2D of local A, B (C too when beta != 0) into arenas owned by
@@ -188,6 +199,13 @@ COSMA_B200_API int cosma_b200_dmultiply_using_layout(void* comm, const char* tra
 COSMA_B200_API int cosma_b200_zmultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
                                                      const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
                                                      const cosma_b200_layout* C, void* stream);
+/* single precision: float / complex-float blocks; alpha and beta are still passed as doubles (converted to float) */
+COSMA_B200_API int cosma_b200_smultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
+                                                     const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                                     const cosma_b200_layout* C, void* stream);
+COSMA_B200_API int cosma_b200_cmultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
+                                                     const cosma_b200_layout* A, const cosma_b200_layout* B, const double* beta,
+                                                     const cosma_b200_layout* C, void* stream);
 
 /* After a synchronised ?multiply_using_layout / p?gemm on `comm`: device milliseconds of its three phases (relayout
  * of A and B in, multiply, relayout of C out), elements moved by this rank's relayouts (in: staying on the rank, sent to
@@ -215,6 +233,14 @@ COSMA_B200_API int cosma_b200_pdgemm(void* grid, char transa, char transb, int m
 COSMA_B200_API int cosma_b200_pzgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const double* a,
                                      int ia, int ja, const int* desca, const double* b, int ib, int jb, const int* descb,
                                      const double* beta, double* c, int ic, int jc, const int* descc, void* stream);
+
+/* psgemm_ / pcgemm_: float / complex-float local arrays; alpha and beta passed as doubles (converted to float). */
+COSMA_B200_API int cosma_b200_psgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const float* a,
+                                     int ia, int ja, const int* desca, const float* b, int ib, int jb, const int* descb,
+                                     const double* beta, float* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pcgemm(void* grid, char transa, char transb, int m, int n, int k, const double* alpha, const float* a,
+                                     int ia, int ja, const int* desca, const float* b, int ib, int jb, const int* descb,
+                                     const double* beta, float* c, int ic, int jc, const int* descc, void* stream);
 
 /* ---- local GEMM with HOST operands ('N','N') -------------------------------------------------
  * Same contract as the reference's GPU base case, which receives host pointers and streams tiles

@@ -119,7 +119,7 @@ def test_single_gpu_transform(lib, dtype, op):
             assert (pad == 55).all()
 
 
-@pytest.mark.parametrize("dtype", ["d", "z"])
+@pytest.mark.parametrize("dtype", ["d", "z", "s", "c"])
 @pytest.mark.parametrize("ta,tb", [("N", "N"), ("T", "N"), ("N", "C"), ("C", "T")])
 def test_single_gpu_multiply_using_layout(lib, dtype, ta, tb):
     """tests/multiply_using_layout.cpp on one rank, plus transposes: custom block layouts in, dense oracle out."""
@@ -127,7 +127,7 @@ def test_single_gpu_multiply_using_layout(lib, dtype, ta, tb):
     comm = init_comm()
     rng = np.random.default_rng(ord(ta) * 7 + ord(tb))
     for (m, n, k, alpha, beta) in ((100, 80, 60, 1.0, 1.0), (257, 130, 95, 2.0, 0.0), (64, 64, 64, 1.0, -1.0)):
-        if dtype == "z":
+        if dtype in "zc":
             alpha = alpha * (1 - 0.5j)
         A = sim.random_values(rng, (m, k) if ta == "N" else (k, m), dtype)
         B = sim.random_values(rng, (k, n) if tb == "N" else (n, k), dtype)
@@ -139,8 +139,9 @@ def test_single_gpu_multiply_using_layout(lib, dtype, ta, tb):
         gA, gB, gC = DeviceDist(dA), DeviceDist(dB), DeviceDist(dC)
         costa.multiply_using_layout(comm, dtype, ta, tb, alpha, gA.layout(0), gB.layout(0), beta, gC.layout(0))
         torch.cuda.synchronize()
-        want = alpha * (sim.apply_op(A, ta) @ sim.apply_op(B, tb)) + (beta * C if beta != 0.0 else 0)
-        assert np.array_equal(gC.download(), want)
+        wide = np.complex128 if dtype in "zc" else np.float64
+        want = alpha * (sim.apply_op(A, ta).astype(wide) @ sim.apply_op(B, tb).astype(wide)) + (beta * C.astype(wide) if beta != 0.0 else 0)
+        assert np.array_equal(gC.download(), want.astype(C.dtype))
     comm.destroy()
 
 
@@ -161,7 +162,7 @@ def _pxgemm_case(comm, grid, case, dtype, nprow, npcol, order, host_pointers, ga
     rank, P = comm.rank, comm.size
     m, n, k, ta, tb = case["m"], case["n"], case["k"], case["ta"], case["tb"]
     alpha, beta = case["alpha"], case["beta"]
-    if dtype == "z" and alpha not in (0.0,):
+    if dtype in "zc" and alpha not in (0.0,):
         alpha = alpha * (1 + 0.5j)
     extra = case.get("extra", 0)
     (ia, ja), (ib, jb), (ic, jc) = case.get("sub", ((1, 1), (1, 1), (1, 1)))
@@ -192,14 +193,15 @@ def _pxgemm_case(comm, grid, case, dtype, nprow, npcol, order, host_pointers, ga
         bc[2].gather_into(got, all_c[r], r)
     want = G[2].copy()
     if m and n:
-        As = sim.apply_op(G[0][ia - 1:ia - 1 + am, ja - 1:ja - 1 + an], ta)
-        Bs = sim.apply_op(G[1][ib - 1:ib - 1 + bm, jb - 1:jb - 1 + bn], tb)
+        wide = np.complex128 if dtype in "zc" else np.float64
+        As = sim.apply_op(G[0][ia - 1:ia - 1 + am, ja - 1:ja - 1 + an], ta).astype(wide)
+        Bs = sim.apply_op(G[1][ib - 1:ib - 1 + bm, jb - 1:jb - 1 + bn], tb).astype(wide)
         prod = alpha * (As @ Bs) if k and alpha != 0 else 0
-        want[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = prod + (beta * G[2][ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] if beta != 0.0 else 0)
+        want[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = np.asarray(prod + (beta * G[2][ic - 1:ic - 1 + m, jc - 1:jc - 1 + n].astype(wide) if beta != 0.0 else 0)).astype(want.dtype)
     return bool(np.array_equal(got, want))
 
 
-@pytest.mark.parametrize("dtype", ["d", "z"])
+@pytest.mark.parametrize("dtype", ["d", "z", "s", "c"])
 @pytest.mark.parametrize("host_pointers", [False, True])
 def test_single_gpu_pxgemm(lib, dtype, host_pointers):
     from cosma_b200.distributed import init_comm
@@ -266,7 +268,7 @@ def _worker(rank, world, port, nprow, npcol, q):
     # (2) p?gemm on a block-cyclic grid
     for order in ("R", "C"):
         grid = costa.Grid(comm, order, nprow, npcol)
-        for dtype in ("d", "z"):
+        for dtype in ("d", "z", "s", "c"):
             for host in (False, True):
                 for case in PX_CASES:
                     ok.append(_pxgemm_case(comm, grid, case, dtype, nprow, npcol, order, host, gather))

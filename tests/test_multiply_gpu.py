@@ -15,26 +15,33 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+NPDT = {"d": np.float64, "z": np.complex128, "s": np.float32, "c": np.complex64}
+
+
 def _globals(m, n, k, dtype, seed=11):
+    """Integer-valued inputs: exact in FP64 and, below 2^24, in FP32 / 3xTF32 as well -> bit-exact comparisons."""
     rng = np.random.default_rng(seed)
     def r(a, b):
         v = rng.integers(0, 10, size=(a, b)).astype(np.float64)
-        if dtype == "z":
+        if dtype in "zc":
             v = v + 1j * rng.integers(0, 10, size=(a, b))
-        return v.astype(np.complex128 if dtype == "z" else np.float64)
+        return v.astype(NPDT[dtype])
     return r(m, k), r(k, n), r(m, n)
 
 
 def _dense_oracle(oracle, Ag, Bg, Cg, alpha, beta):
     m, k = Ag.shape
     n = Bg.shape[1]
+    if Ag.dtype in (np.float32, np.complex64):  # exact integers: form the expected result in double, then narrow
+        wide = np.complex128 if Ag.dtype == np.complex64 else np.float64
+        return (alpha * (Ag.astype(wide) @ Bg.astype(wide)) + beta * Cg.astype(wide)).astype(Ag.dtype)
     C = np.ascontiguousarray(Cg.T).reshape(-1).copy()
     out = oracle.gemm("N", "N", m, n, k, alpha, np.ascontiguousarray(Ag.T).reshape(-1), m, np.ascontiguousarray(Bg.T).reshape(-1), k,
                       beta, C, m)
     return out.reshape(n, m).T
 
 
-@pytest.mark.parametrize("dtype", ["d", "z"])
+@pytest.mark.parametrize("dtype", ["d", "z", "s", "c"])
 @pytest.mark.parametrize("m,n,k,steps,alpha,beta", [
     (256, 192, 320, "", 1.0, 0.0),
     (300, 200, 100, "sm2,sn2,sk2", 1.0, 1.0),       # sequential steps: bucket offsets, beta = 1 from the 2nd k chunk on
@@ -113,22 +120,23 @@ def _worker(rank, world, port, cases, q):
             pl.multiply(alpha, beta)
         torch.cuda.synchronize()
         # gather the local C buffers on rank 0 through torch.distributed (test plumbing only)
-        tdt = torch.complex128 if dtype == "z" else torch.float64
+        tdt = {"d": torch.float64, "z": torch.complex128, "s": torch.float32, "c": torch.complex64}[dtype]
         sizes = [sum((b[1] - b[0] + 1) * (b[3] - b[2] + 1) for b in pl.local_blocks("C", r)) for r in range(world)]
         mx = max(max(sizes), 1)
         mine = torch.zeros(mx, dtype=tdt, device="cuda")
         if not pl.idle:
             mine[:pl.C.initial] = pl.C.local
-        real = torch.view_as_real(mine).reshape(-1) if dtype == "z" else mine
+        real = torch.view_as_real(mine).reshape(-1) if dtype in "zc" else mine
         allb = [torch.empty_like(real) for _ in range(world)]
         dist.all_gather(allb, real)
         if rank == 0:
             got = np.zeros((m, n), dtype=Cg.dtype)
             for r in range(pl.P_used):
                 loc = allb[r].cpu().numpy()
-                loc = loc.view(np.complex128) if dtype == "z" else loc
+                loc = loc.view(NPDT[dtype]) if dtype in "zc" else loc
                 gather_local_to_global(pl, "C", loc, got, rank=r)
-            results.append((got, alpha * (Ag @ Bg) + beta * Cg))
+            wide = np.complex128 if dtype in "zc" else np.float64
+            results.append((got, (alpha * (Ag.astype(wide) @ Bg.astype(wide)) + beta * Cg.astype(wide)).astype(Cg.dtype)))
         pl.destroy()
     if rank == 0:
         q.put([bool(np.array_equal(g, w)) for g, w in results])
@@ -162,6 +170,8 @@ def test_two_gpus(lib):
         (300, 260, 220, "sm2,pn2,sk3", "d", 2.0, 1.0),      # several buckets per rank -> exact-count grouped send/recv
         (257, 129, 511, "pk2", "d", 1.0, 1.0),              # irregular k split, beta != 0 -> staged reduce + axpby
         (256, 256, 256, "pk2", "z", 1.0 - 0.5j, 0.5j),
+        (512, 384, 256, "pk2", "s", 1.0, 1.0),              # single precision: 3xTF32 tcgen05 base case, float NCCL reduce
+        (300, 260, 220, "sm2,pn2,sk3", "c", 2.0, 1.0),
     ])
 
 
@@ -171,6 +181,7 @@ def test_four_gpus(lib):
         (100, 100, 100, "pm2,pk2", "d", 1.0, 1.0),          # reference tests/multiply.cpp case
         (20, 30, 25, "sm2,sn2,pk2,pm2", "d", 1.0, 1.0),
         (400, 400, 400, "", "z", 1.0, 0.0),
+        (512, 512, 512, "pn2,pk2", "s", 1.0, 0.0),
     ])
 
 
@@ -182,4 +193,6 @@ def test_eight_gpus(lib):
         (200, 200, 200, "sk3,sm3,sn3,pk2,pn2,pm2", "d", 1.0, 1.0),  # tests/multiply.cpp
         (512, 32, 736, "pk2,pm2,pk2", "d", 1.0, 1.0),               # tests/multiply.cpp (nested k reductions)
         (1000, 1000, 1000, "pm2,pn2,pk2", "z", 1.0, 1.0),
+        (1024, 1024, 1024, "pm2,pn2,pk2", "s", 1.0, 0.0),
+        (100, 100, 100, "sm2,pn2,sk2,pm2,sn2,pk2", "c", 1.0, 1.0),  # tests/scalar_matmul.cpp, complex<float>
     ])
