@@ -235,3 +235,105 @@ def ref_transform_p1(dtype, from_layout, to_layout, trans, alpha, beta):
                             ctypes.c_char(to_layout[4].encode()), ctypes.c_char(trans.encode()), al, be)
     if rc != 0:
         raise RuntimeError("reference costa::transform failed (%d)" % rc)
+
+
+# ---- the unmodified reference on SEVERAL ranks (oracle/minirun.py + stubs/minimpi.cpp + oracle/ref_driver.cpp) --------
+REF_DRIVER = os.path.join(HERE, "_ref", "ref_driver")
+NPDT = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+
+
+def have_ref_driver():
+    return os.path.exists(REF_DRIVER) and have_ref()
+
+
+def _scalar_arg(v):
+    v = complex(v)
+    return "%r,%r" % (v.real, v.imag)
+
+
+def _run_driver(nranks, args, threads=1, timeout=600):
+    import sys
+    sys.path.insert(0, HERE)
+    from minirun import launch
+    argv = [REF_DRIVER] + ["%s=%s" % kv for kv in args.items()]
+    code, outs = launch(nranks, argv, threads=threads, stdout=subprocess.PIPE, timeout=timeout)
+    if code != 0:
+        raise RuntimeError("reference driver failed with exit code %s: %s" % (code, " ".join(argv)))
+    text = outs[0].decode()
+    return [float(line.split()[1]) for line in text.splitlines() if line.startswith("REF_TIME_MS")]
+
+
+def ref_multiply_ranks(dtype, m, n, k, P, steps, alpha, beta, A, B, C, threads=1, reps=1, tmpdir=None):
+    """cosma::multiply of the unmodified reference on P minimpi ranks. A (m x k), B (k x n), C (m x n): dense numpy
+    arrays. Returns (list of per-rank raw local C buffers -- ranks idle under the strategy give None --, times in ms)."""
+    import tempfile
+    with tempfile.TemporaryDirectory(dir=tmpdir) as d:
+        dt = NPDT[dtype]
+        for name, M in (("A", A), ("B", B), ("C", C)):
+            np.asfortranarray(M.astype(dt)).T.tofile(os.path.join(d, name + ".bin"))  # column-major bytes
+        times = _run_driver(P, dict(op="multiply", dtype=dtype, m=m, n=n, k=k, steps=steps or "auto", alpha=_scalar_arg(alpha),
+                                    beta=_scalar_arg(beta), dir=d, reps=reps), threads=threads)
+        outs = []
+        for r in range(P):
+            f = os.path.join(d, "Cout.%d.bin" % r)
+            outs.append(np.fromfile(f, dtype=dt) if os.path.exists(f) else None)
+    return outs, times
+
+
+def _desc_arg(desc):
+    # 9-int ScaLAPACK descriptor -> "M,N,MB,NB,RSRC,CSRC,LLD"
+    return ",".join(str(int(desc[i])) for i in (2, 3, 4, 5, 6, 7, 8))
+
+
+def _llds(descs):
+    return ",".join(str(int(x[8])) for x in descs)
+
+
+def ref_pxgemm_ranks(dtype, order, nprow, npcol, ta, tb, m, n, k, alpha, a_loc, ia, ja, desca, b_loc, ib, jb, descb, beta, c_loc, ic, jc,
+                     descc, threads=1, reps=1):
+    """cosma::pxgemm<T> of the unmodified reference on nprow*npcol minimpi ranks (miniblacs grid). a_loc/b_loc/c_loc:
+    per-rank local arrays (1-D numpy, LLD x local columns); desc*: per-rank descriptors (LLD may differ). Returns
+    (per-rank local C arrays after the call, times in ms)."""
+    import tempfile
+    P = nprow * npcol
+    dt = NPDT[dtype]
+    with tempfile.TemporaryDirectory() as d:
+        for r in range(P):
+            for name, loc in (("a", a_loc), ("b", b_loc), ("c", c_loc)):
+                np.ascontiguousarray(loc[r], dtype=dt).tofile(os.path.join(d, "%s.%d.bin" % (name, r)))
+        times = _run_driver(P, dict(op="pxgemm", dtype=dtype, ta=ta, tb=tb, m=m, n=n, k=k, alpha=_scalar_arg(alpha), beta=_scalar_arg(beta),
+                                    ia=ia, ja=ja, ib=ib, jb=jb, ic=ic, jc=jc, order=order, nprow=nprow, npcol=npcol,
+                                    desca=_desc_arg(desca[0]), descb=_desc_arg(descb[0]), descc=_desc_arg(descc[0]), llda=_llds(desca),
+                                    lldb=_llds(descb), lldc=_llds(descc), dir=d, reps=reps),
+                            threads=threads)
+        outs = [np.fromfile(os.path.join(d, "cout.%d.bin" % r), dtype=dt) for r in range(P)]
+    return outs, times
+
+
+def ref_pxgemr2d_ranks(dtype, order, nprow, npcol, m, n, a_loc, ia, ja, desca, c_loc, ic, jc, descc, orderc=None):
+    """costa::pxgemr2d<T> of the unmodified reference. Returns the per-rank local C arrays."""
+    import tempfile
+    P = nprow * npcol
+    dt = NPDT[dtype]
+    with tempfile.TemporaryDirectory() as d:
+        for r in range(P):
+            for name, loc in (("a", a_loc), ("c", c_loc)):
+                np.ascontiguousarray(loc[r], dtype=dt).tofile(os.path.join(d, "%s.%d.bin" % (name, r)))
+        _run_driver(P, dict(op="pxgemr2d", dtype=dtype, m=m, n=n, ia=ia, ja=ja, ic=ic, jc=jc, order=order, orderc=orderc or order, nprow=nprow,
+                            npcol=npcol, desca=_desc_arg(desca[0]), descc=_desc_arg(descc[0]), llda=_llds(desca), lldc=_llds(descc), dir=d))
+        return [np.fromfile(os.path.join(d, "cout.%d.bin" % r), dtype=dt) for r in range(P)]
+
+
+def ref_pxtran_ranks(dtype, order, nprow, npcol, trans, m, n, alpha, a_loc, ia, ja, desca, beta, c_loc, ic, jc, descc):
+    """costa::pxtran_op<T> of the unmodified reference: sub(C) (m x n) = beta*sub(C) + alpha*op(sub(A)) (n x m)."""
+    import tempfile
+    P = nprow * npcol
+    dt = NPDT[dtype]
+    with tempfile.TemporaryDirectory() as d:
+        for r in range(P):
+            for name, loc in (("a", a_loc), ("c", c_loc)):
+                np.ascontiguousarray(loc[r], dtype=dt).tofile(os.path.join(d, "%s.%d.bin" % (name, r)))
+        _run_driver(P, dict(op="pxtran", dtype=dtype, trans=trans, m=m, n=n, alpha=_scalar_arg(alpha), beta=_scalar_arg(beta), ia=ia, ja=ja, ic=ic,
+                            jc=jc, order=order, nprow=nprow, npcol=npcol, desca=_desc_arg(desca[0]), descc=_desc_arg(descc[0]), llda=_llds(desca),
+                            lldc=_llds(descc), dir=d))
+        return [np.fromfile(os.path.join(d, "cout.%d.bin" % r), dtype=dt) for r in range(P)]

@@ -50,8 +50,9 @@ def reduce_slices(op, member_src, g):
     return np.concatenate(outs) if outs else np.zeros(0)
 
 
-def simulate(m, n, k, P, steps, alpha=1.0, beta=0.0, dtype="d", seed=0, ints=True):
-    """Returns (C_got, C_want, plans) as dense m x n arrays."""
+def simulate(m, n, k, P, steps, alpha=1.0, beta=0.0, dtype="d", seed=0, ints=True, inputs=None, local_c=None):
+    """Returns (C_got, C_want, P_used) with C as dense m x n arrays. inputs = (A, B, C) overrides the random operands;
+    local_c (a list) receives every rank's raw local C buffer (matrix_pointer() contents; None for idle ranks)."""
     rng = np.random.default_rng(seed)
     npdt = np.float64 if dtype == "d" else np.complex128
     def rnd(r, c):
@@ -60,6 +61,8 @@ def simulate(m, n, k, P, steps, alpha=1.0, beta=0.0, dtype="d", seed=0, ints=Tru
             v = v + 1j * (rng.integers(0, 10, size=(r, c)) if ints else rng.random((r, c)))
         return v.astype(npdt)
     Ag, Bg, Cg = rnd(m, k), rnd(k, n), rnd(m, n)
+    if inputs is not None:
+        Ag, Bg, Cg = (np.asarray(x, dtype=npdt) for x in inputs)
     plans = [MultiplyPlan(None, m, n, k, steps, dtype, rank=r, nranks=P, allocate=False) for r in range(P)]
     P_used = plans[0].P_used
     arenas = []
@@ -117,6 +120,8 @@ def simulate(m, n, k, P, steps, alpha=1.0, beta=0.0, dtype="d", seed=0, ints=Tru
     for r in range(P_used):
         gather_local_to_global(plans[r], "C", arenas[r][2], got)
     want = alpha * (Ag @ Bg) + beta * Cg
+    if local_c is not None:
+        local_c.extend(arenas[r][2][:plans[r].initial_elements[2]].copy() if r < P_used else None for r in range(P))
     for pl in plans:
         pl.destroy()
     return got, want, P_used
