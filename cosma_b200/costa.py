@@ -58,6 +58,8 @@ def _declare(lib):
     lib.cosma_b200_grid_info.argtypes = [vp, pi, pi, pi, pi]
     for name in ("cosma_b200_p%sgemm" % t for t in "sdcz"):
         getattr(lib, name).argtypes = [vp, ctypes.c_char, ctypes.c_char, ci, ci, ci, pd, vp, ci, ci, pi, vp, ci, ci, pi, pd, vp, ci, ci, pi, vp]
+    lib.cosma_b200_pxtran.argtypes = [vp, ctypes.c_char, ctypes.c_char, ci, ci, pd, vp, ci, ci, pi, pd, vp, ci, ci, pi, vp]
+    lib.cosma_b200_pxgemr2d.argtypes = [vp, vp, ctypes.c_char, ci, ci, vp, ci, ci, pi, vp, ci, ci, pi, vp]
     lib.cosma_b200_last_layout_multiply_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i64), cp, ci, pi]
     lib._costa_declared = True
 
@@ -267,3 +269,23 @@ def last_layout_multiply_stats(comm):
     _lib.check(L.cosma_b200_last_layout_multiply_stats(comm.handle, ms, el, buf, 256, ctypes.byref(n)), "cosma_b200_last_layout_multiply_stats")
     return {"ms_relayout_in": ms[0], "ms_multiply": ms[1], "ms_relayout_out": ms[2], "in_local_elements": el[0], "in_remote_elements": el[1],
             "out_local_elements": el[2], "out_remote_elements": el[3], "strategy": buf.value.decode(), "launches": n.value}
+
+
+def pxtran(grid, dtype, op, m, n, alpha, a, ia, ja, desca, beta, c, ic, jc, descc, stream=None):
+    """p?tran / p?tranu (op 'T') / p?tranc (op 'C') (reference libs/COSTA/src/costa/pxtran/pxtran.h:7-20,
+    pxtran_op/costa_pxtran_op.cpp:14-172): sub(C) (m x n) = beta*sub(C) + alpha*op(sub(A)) (sub(A) is n x m).
+    a, c: addresses of the rank's local arrays (device or host)."""
+    L = lib()
+    al, be = _scalars([alpha], dtype, 1), _scalars([beta], dtype, 1)
+    da, dc = (np.ascontiguousarray(d, dtype=np.int32) for d in (desca, descc))
+    _lib.check(L.cosma_b200_pxtran(grid.handle, dtype.encode(), op.encode(), m, n, al, vp(a), ia, ja, da.ctypes.data_as(pi), be, vp(c), ic, jc,
+                                   dc.ctypes.data_as(pi), _stream_ptr(stream)), "cosma_b200_pxtran")
+
+
+def pxgemr2d(grid_a, grid_c, dtype, m, n, a, ia, ja, desca, c, ic, jc, descc, stream=None):
+    """p?gemr2d (reference libs/COSTA/src/costa/pxgemr2d/pxgemr2d.h:7-41, costa_pxgemr2d.cpp:14-168): sub(C) = sub(A)
+    between two block-cyclic distributions (possibly on different process grids of one communicator)."""
+    L = lib()
+    da, dc = (np.ascontiguousarray(d, dtype=np.int32) for d in (desca, descc))
+    _lib.check(L.cosma_b200_pxgemr2d(grid_a.handle, grid_c.handle, dtype.encode(), m, n, vp(a), ia, ja, da.ctypes.data_as(pi), vp(c), ic, jc,
+                                     dc.ctypes.data_as(pi), _stream_ptr(stream)), "cosma_b200_pxgemr2d")

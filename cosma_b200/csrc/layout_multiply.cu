@@ -61,7 +61,17 @@ struct Grid {
     // device staging for host-resident operands (N4), grown on demand
     char* stage[3] = {nullptr, nullptr, nullptr};
     size_t stage_bytes[3] = {0, 0, 0};
+    // transform plans of p?tran / p?gemr2d keyed by descriptors, pointers, op and scalars (small LRU)
+    struct Cached {
+        std::string key;
+        std::unique_ptr<TransformPlan> plan;
+        std::uint64_t stamp = 0;
+    };
+    std::vector<Cached> transforms;
+    std::uint64_t clock = 0;
+    int last_launches = 0;
     ~Grid() {
+        transforms.clear();
         for (auto& s : stage)
             if (s) cudaFree(s);
     }
@@ -435,5 +445,139 @@ int cosma_b200_pcgemm(void* grid, char transa, char transb, int m, int n, int k,
                       const int* descc, void* stream) {
     return xpgemm(grid, 'c', transa, transb, m, n, k, alpha, a, ia, ja, desca, b, ib, jb, descb, beta, c, ic, jc, descc, stream);
 }
+
+// ---- p?tran / p?tranu / p?tranc and p?gemr2d ------------------------------------------------------
+// Reference: libs/COSTA/src/costa/pxtran_op/costa_pxtran_op.cpp:14-172 (sub(C) = beta*sub(C) + alpha*op(sub(A)), sub(C) is
+// m x n and sub(A) n x m) and pxgemr2d/costa_pxgemr2d.cpp:14-168 (sub(C) = sub(A) between two process grids). Both are one
+// costa::transform between two block-cyclic layouts: the same plan + R3/R4 kernels + NCCL exchange as p?gemm's relayouts.
+static int xptransform(Grid* ga, Grid* gc, char dtype, char op, int m, int n, const double* alpha, const void* a, int ia, int ja,
+                       const int* desca, const double* beta, void* c, int ic, int jc, const int* descc, cudaStream_t stream) {
+    if (!ga || !gc || !desca || !descc || !alpha || !beta || ga->comm != gc->comm) return COSMA_B200_INVALID_ARG;
+    try {
+        const bool cplx = dtype == 'c' || dtype == 'z';
+        const int eb = dtype_bytes(dtype);
+        if (eb == 0) return COSMA_B200_INVALID_ARG;
+        op = std::toupper(op);
+        if (op != 'N' && op != 'T' && op != 'C') return COSMA_B200_INVALID_ARG;
+        if (m == 0 || n == 0) return COSMA_B200_OK;
+        Comm* comm = gc->comm;
+        const int rank = comm->rank;
+        Grid* grids[2] = {ga, gc};
+        const void* user[2] = {a, c};
+        const int* desc[2] = {desca, descc};
+        void* dev[2] = {const_cast<void*>(a), c};
+        bool staged[2] = {false, false}, in_grid[2];
+        size_t local_bytes[2] = {0, 0};
+        const bool c_whole = ic == 1 && jc == 1 && m == descc[2] && n == descc[3];
+        for (int x = 0; x < 2; ++x) {
+            Grid* g = grids[x];
+            in_grid[x] = rank < g->nprow * g->npcol;
+            if (!in_grid[x] || !user[x] || !is_host_pointer(user[x])) continue;
+            int myrow = 0, mycol = 0;
+            costa::rank_to_grid(rank, g->nprow, g->npcol, g->order, &myrow, &mycol);
+            const int loc_cols = costa::numroc(desc[x][3], desc[x][5], mycol, desc[x][7], g->npcol);
+            local_bytes[x] = static_cast<size_t>(desc[x][8]) * std::max(loc_cols, 0) * eb;
+            if (local_bytes[x] == 0) continue;
+            const int slot = x == 0 ? 0 : 2;  // staging slots of the C grid: [0] source, [2] destination
+            if (gc->stage_bytes[slot] < local_bytes[x]) {
+                if (gc->stage[slot]) { cudaStreamSynchronize(stream); cudaFree(gc->stage[slot]); gc->stage[slot] = nullptr; gc->stage_bytes[slot] = 0; }
+                if (cudaMalloc(reinterpret_cast<void**>(&gc->stage[slot]), local_bytes[x]) != cudaSuccess) {
+                    set_last_error("p?tran / p?gemr2d: cudaMalloc of a staging buffer failed");
+                    return COSMA_B200_OUT_OF_MEMORY;
+                }
+                gc->stage_bytes[slot] = local_bytes[x];
+            }
+            staged[x] = true;
+            dev[x] = gc->stage[slot];
+            const bool upload = x == 0 || !(is_zero(beta, cplx) && c_whole);
+            if (upload) COSMA_B200_CUDA_TRY(cudaMemcpyAsync(dev[x], user[x], local_bytes[x], cudaMemcpyHostToDevice, stream));
+        }
+        const int a_subm = op == 'N' ? m : n, a_subn = op == 'N' ? n : m;
+        costa::grid_layout LA = costa::get_scalapack_layout(desca[8], desca[2], desca[3], ia, ja, a_subm, a_subn, desca[4], desca[5], ga->nprow,
+                                                            ga->npcol, ga->order, desca[6], desca[7], dev[0], eb, 'C', in_grid[0] ? rank : -1);
+        costa::grid_layout LC = costa::get_scalapack_layout(descc[8], descc[2], descc[3], ic, jc, m, n, descc[4], descc[5], gc->nprow, gc->npcol,
+                                                            gc->order, descc[6], descc[7], dev[1], eb, 'C', in_grid[1] ? rank : -1);
+        LA.grid.n_ranks = LC.grid.n_ranks = comm->size;
+        std::string key;
+        key.push_back(dtype); key.push_back(op);
+        append(key, alpha, (cplx ? 2 : 1) * sizeof(double));
+        append(key, beta, (cplx ? 2 : 1) * sizeof(double));
+        append_layout(key, LA);
+        append_layout(key, LC);
+        Grid::Cached* entry = nullptr;
+        for (auto& e : gc->transforms)
+            if (e.key == key) entry = &e;
+        if (!entry) {
+            if (gc->transforms.size() >= kMaxCachedTransforms) {
+                size_t oldest = 0;
+                for (size_t i = 1; i < gc->transforms.size(); ++i)
+                    if (gc->transforms[i].stamp < gc->transforms[oldest].stamp) oldest = i;
+                cudaStreamSynchronize(stream);  // the evicted plan may still be running
+                gc->transforms.erase(gc->transforms.begin() + oldest);
+            }
+            Grid::Cached e;
+            e.key = key;
+            std::vector<costa::transform_spec> spec(1);
+            spec[0].from = &LA; spec[0].to = &LC; spec[0].op = op;
+            spec[0].alpha[0] = alpha[0]; spec[0].alpha[1] = cplx ? alpha[1] : 0.0;
+            spec[0].beta[0] = beta[0]; spec[0].beta[1] = cplx ? beta[1] : 0.0;
+            int rc = transform_plan_build(comm, rank, comm->size, dtype, spec, e.plan);
+            if (rc != COSMA_B200_OK) return rc;
+            gc->transforms.push_back(std::move(e));
+            entry = &gc->transforms.back();
+        }
+        entry->stamp = ++gc->clock;
+        int rc = transform_plan_run(*entry->plan, stream);
+        if (rc != COSMA_B200_OK) return rc;
+        gc->last_launches = entry->plan->last_launches;
+        if (staged[1]) COSMA_B200_CUDA_TRY(cudaMemcpyAsync(c, dev[1], local_bytes[1], cudaMemcpyDeviceToHost, stream));
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+int cosma_b200_pxtran(void* grid, char dtype, char op, int m, int n, const double* alpha, const void* a, int ia, int ja, const int* desca,
+                      const double* beta, void* c, int ic, int jc, const int* descc, void* stream) {
+    op = std::toupper(op);
+    if (op != 'T' && op != 'C') return COSMA_B200_INVALID_ARG;
+    return xptransform(static_cast<Grid*>(grid), static_cast<Grid*>(grid), dtype, op, m, n, alpha, a, ia, ja, desca, beta, c, ic, jc, descc,
+                       static_cast<cudaStream_t>(stream));
+}
+int cosma_b200_pxgemr2d(void* grid_a, void* grid_c, char dtype, int m, int n, const void* a, int ia, int ja, const int* desca, void* c, int ic,
+                        int jc, const int* descc, void* stream) {
+    const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+    return xptransform(static_cast<Grid*>(grid_a), static_cast<Grid*>(grid_c), dtype, 'N', m, n, one, a, ia, ja, desca, zero, c, ic, jc, descc,
+                       static_cast<cudaStream_t>(stream));
+}
+int cosma_b200_grid_last_launches(void* grid) { return grid ? static_cast<Grid*>(grid)->last_launches : 0; }
+
+#define COSMA_B200_PTRAN(NAME, T, DT, OP)                                                                                              \
+    int cosma_b200_##NAME(void* grid, int m, int n, const T* alpha, const T* a, int ia, int ja, const int* desca, const T* beta, T* c,   \
+                          int ic, int jc, const int* descc, void* stream) {                                                            \
+        if (!alpha || !beta) return COSMA_B200_INVALID_ARG;                                                                           \
+        const bool cplx = DT == 'c' || DT == 'z';                                                                                     \
+        const double a2[2] = {double(alpha[0]), cplx ? double(alpha[1]) : 0.0}, b2[2] = {double(beta[0]), cplx ? double(beta[1]) : 0.0}; \
+        return cosma_b200_pxtran(grid, DT, OP, m, n, a2, a, ia, ja, desca, b2, c, ic, jc, descc, stream);                             \
+    }
+COSMA_B200_PTRAN(pstran, float, 's', 'T')
+COSMA_B200_PTRAN(pdtran, double, 'd', 'T')
+COSMA_B200_PTRAN(pctranu, float, 'c', 'T')
+COSMA_B200_PTRAN(pztranu, double, 'z', 'T')
+COSMA_B200_PTRAN(pctranc, float, 'c', 'C')
+COSMA_B200_PTRAN(pztranc, double, 'z', 'C')
+#undef COSMA_B200_PTRAN
+
+#define COSMA_B200_PGEMR2D(NAME, T, DT)                                                                                               \
+    int cosma_b200_##NAME(void* grid_a, void* grid_c, int m, int n, const T* a, int ia, int ja, const int* desca, T* c, int ic, int jc, \
+                          const int* descc, void* stream) {                                                                            \
+        return cosma_b200_pxgemr2d(grid_a, grid_c, DT, m, n, a, ia, ja, desca, c, ic, jc, descc, stream);                             \
+    }
+COSMA_B200_PGEMR2D(psgemr2d, float, 's')
+COSMA_B200_PGEMR2D(pdgemr2d, double, 'd')
+COSMA_B200_PGEMR2D(pcgemr2d, float, 'c')
+COSMA_B200_PGEMR2D(pzgemr2d, double, 'z')
+#undef COSMA_B200_PGEMR2D
 
 }  // extern "C"

@@ -242,6 +242,42 @@ COSMA_B200_API int cosma_b200_pcgemm(void* grid, char transa, char transb, int m
                                      int ia, int ja, const int* desca, const float* b, int ib, int jb, const int* descb,
                                      const double* beta, float* c, int ic, int jc, const int* descc, void* stream);
 
+/* ---- ScaLAPACK p?tran / p?tranu / p?tranc and p?gemr2d (COSTA's wrappers) ---------------------------------
+ * p?tran*: sub(C) = beta*sub(C) + alpha*op(sub(A)); sub(C) = C(ic:ic+m-1, jc:jc+n-1), sub(A) = A(ia:ia+n-1, ja:ja+m-1);
+ *   op = transpose (p{s,d}tran, p{c,z}tranu) or conjugate transpose (p{c,z}tranc). Reference: libs/COSTA/src/costa/pxtran/
+ *   pxtran.h:7-20, pxtranu/pxtranu.h:7-20, pxtranc/pxtranc.h:7-20 -> costa::pxtran_op (pxtran_op/costa_pxtran_op.cpp:14-172).
+ * p?gemr2d: sub(C) = sub(A) (m x n) between two block-cyclic distributions, possibly on different process grids of the same
+ *   communicator. Reference: pxgemr2d/pxgemr2d.h:7-41 -> costa::pxgemr2d (pxgemr2d/costa_pxgemr2d.cpp:14-168); the trailing
+ *   BLACS context argument of the reference is replaced by the two grid handles.
+ * Same conventions as p?gemm: `grid` from cosma_b200_grid_create, 9-int descriptors, 1-based sub-matrix origins, local arrays
+ * as DEVICE or HOST pointers, beta == 0 never reads C, pure data movement (alpha = 1, beta = 0) is bit-exact. One
+ * costa::transform plan per (descriptors, pointers, op, scalars) is cached in the grid. */
+COSMA_B200_API int cosma_b200_pxtran(void* grid, char dtype, char op, int m, int n, const double* alpha, const void* a, int ia, int ja,
+                                     const int* desca, const double* beta, void* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pxgemr2d(void* grid_a, void* grid_c, char dtype, int m, int n, const void* a, int ia, int ja, const int* desca,
+                                       void* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pstran(void* grid, int m, int n, const float* alpha, const float* a, int ia, int ja, const int* desca,
+                                     const float* beta, float* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pdtran(void* grid, int m, int n, const double* alpha, const double* a, int ia, int ja, const int* desca,
+                                     const double* beta, double* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pctranu(void* grid, int m, int n, const float* alpha, const float* a, int ia, int ja, const int* desca,
+                                      const float* beta, float* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pztranu(void* grid, int m, int n, const double* alpha, const double* a, int ia, int ja, const int* desca,
+                                      const double* beta, double* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pctranc(void* grid, int m, int n, const float* alpha, const float* a, int ia, int ja, const int* desca,
+                                      const float* beta, float* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pztranc(void* grid, int m, int n, const double* alpha, const double* a, int ia, int ja, const int* desca,
+                                      const double* beta, double* c, int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_psgemr2d(void* grid_a, void* grid_c, int m, int n, const float* a, int ia, int ja, const int* desca, float* c,
+                                       int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pdgemr2d(void* grid_a, void* grid_c, int m, int n, const double* a, int ia, int ja, const int* desca, double* c,
+                                       int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pcgemr2d(void* grid_a, void* grid_c, int m, int n, const float* a, int ia, int ja, const int* desca, float* c,
+                                       int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_pzgemr2d(void* grid_a, void* grid_c, int m, int n, const double* a, int ia, int ja, const int* desca, double* c,
+                                       int ic, int jc, const int* descc, void* stream);
+COSMA_B200_API int cosma_b200_grid_last_launches(void* grid);                  /* kernels launched by the last p?tran / p?gemr2d */
+
 /* ---- local GEMM with HOST operands ('N','N') -------------------------------------------------
  * Same contract as the reference's GPU base case, which receives host pointers and streams tiles
  * through the device (gpu::gemm, libs/Tiled-MM/src/Tiled-MM/tiled_mm.cpp:492-624; copy_c_back = true).

@@ -24,6 +24,10 @@
 #include <costa/pxgemr2d/costa_pxgemr2d.hpp>
 #include <costa/pxtran_op/costa_pxtran_op.hpp>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <complex>
 #include <cstdio>
@@ -213,7 +217,20 @@ int dispatch(const Args& a, int rank, int P) {
 }
 }  // namespace
 
+// a crash inside the reference (e.g. SIGFPE) should say where
+static void crash_handler(int sig) {
+    void* frames[48];
+    const int n = backtrace(frames, 48);
+    const char msg[] = "ref_driver: fatal signal inside the reference; backtrace:\n";
+    (void)!write(2, msg, sizeof msg - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+
 int main(int argc, char** argv) {
+    signal(SIGFPE, crash_handler);
+    signal(SIGSEGV, crash_handler);
     MPI_Init(&argc, &argv);
     int rank, P;
     MPI_Comm_rank(MPI_COMM_WORLD, &rank);

@@ -20,6 +20,9 @@ CASES = [  # (m, n, k, P, steps, dtype, alpha, beta)
     (100, 100, 100, 8, "sm2,pn2,sk2,pm2,sn2,pk2", "s", 1.0, -1.0),  # tests/scalar_matmul.cpp
     (64, 64, 64, 8, "pm2,pn2,pk2", "d", 1.0, 0.0),       # the BASELINE 32768^3 P=8 strategy in miniature
     (32, 32, 512, 8, "pk8", "d", 1.0, 0.0),              # the BASELINE large-K strategy in miniature
+    (96, 96, 96, 2, "pk2", "d", 1.0, 0.0),               # BASELINE configs[0] / 32768^3 at P=2 in miniature
+    (60, 52, 44, 2, "sm2,sk3,pn2", "z", 2.0, 1.0),     # (a strategy ENDING in a sequential step makes the reference divide by zero)
+    (64, 64, 64, 4, "pn2,pk2", "d", 1.0, 0.0),           # the BASELINE 32768^3 P=4 strategy in miniature
 ]
 
 

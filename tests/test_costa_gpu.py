@@ -212,6 +212,60 @@ def test_single_gpu_pxgemm(lib, dtype, host_pointers):
     grid.destroy(); comm.destroy()
 
 
+TRAN_CASES = [
+    dict(m=40, n=56, ba=(8, 8), bc=(8, 8), sa=(1, 1), sc=(1, 1), extra=0, alpha=1.0, beta=0.0),
+    dict(m=37, n=53, ba=(5, 7), bc=(4, 9), sa=(3, 2), sc=(2, 6), extra=11, alpha=2.0, beta=-1.0),
+    dict(m=64, n=16, ba=(16, 4), bc=(8, 32), sa=(1, 5), sc=(7, 1), extra=3, alpha=1.0, beta=1.0),
+    dict(m=300, n=200, ba=(32, 32), bc=(64, 16), sa=(1, 1), sc=(1, 1), extra=0, alpha=1.0, beta=0.0),
+]
+
+
+def _pxtran_case(comm, grid, grid2, case, dtype, op, nprow, npcol, order, order2, host_pointers, gather):
+    """One p?tran (op 'T'|'C') or p?gemr2d (op 'N', A on `grid`, C on `grid2`) case; every rank's local C is compared bit for
+    bit with the dense definition scattered back (and, on rank 0, with the live reference wrappers when oracle/_ref exists)."""
+    rank, P = comm.rank, comm.size
+    m, n, extra = case["m"], case["n"], case["extra"]
+    (ia, ja), (ic, jc) = case["sa"], case["sc"]
+    alpha, beta = (case["alpha"], case["beta"]) if op != "N" else (1.0, 0.0)
+    if dtype in "cz" and op != "N":
+        alpha = alpha * (1 - 0.5j)
+    am, an = (m, n) if op == "N" else (n, m)
+    rng = np.random.default_rng(m * 13 + n)
+    GA = sim.random_values(rng, (am + ia - 1 + extra, an + ja - 1 + extra), dtype)
+    GC = sim.random_values(rng, (m + ic - 1 + extra, n + jc - 1 + extra), dtype)
+    bcA = sim.BlockCyclic(GA.shape[0], GA.shape[1], case["ba"][0], case["ba"][1], nprow, npcol, order, 0, 0, lld_pad=2)
+    bcC = sim.BlockCyclic(GC.shape[0], GC.shape[1], case["bc"][0], case["bc"][1], nprow, npcol, order2, 0, 0, lld_pad=1)
+    Cin = GC.copy()
+    if beta == 0.0:
+        Cin[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = np.nan  # must not be read
+    a_loc, c_loc = bcA.scatter(GA, rank, fill=77), bcC.scatter(Cin, rank, fill=55)
+    if host_pointers:
+        bufs = [torch.from_numpy(a_loc).pin_memory(), torch.from_numpy(c_loc).pin_memory()]
+    else:
+        bufs = [_dev(a_loc), _dev(c_loc)]
+    if op == "N":
+        costa.pxgemr2d(grid, grid2, dtype, m, n, bufs[0].data_ptr(), ia, ja, bcA.desc(rank), bufs[1].data_ptr(), ic, jc, bcC.desc(rank))
+    else:
+        costa.pxtran(grid, dtype, op, m, n, alpha, bufs[0].data_ptr(), ia, ja, bcA.desc(rank), beta, bufs[1].data_ptr(), ic, jc, bcC.desc(rank))
+    torch.cuda.synchronize()
+    dense = GC.copy()
+    dense[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = alpha * sim.apply_op(GA[ia - 1:ia - 1 + am, ja - 1:ja - 1 + an], op) + \
+        (beta * GC[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] if beta != 0.0 else 0)
+    want = bcC.scatter(dense.astype(GC.dtype), rank, fill=55)
+    return bool(np.array_equal(bufs[1].cpu().numpy().view(np.uint8), want.view(np.uint8)))
+
+
+@pytest.mark.parametrize("dtype,op", [("d", "T"), ("s", "T"), ("z", "T"), ("z", "C"), ("c", "C"), ("d", "N"), ("z", "N"), ("s", "N"), ("c", "N")])
+@pytest.mark.parametrize("host_pointers", [False, True])
+def test_single_gpu_pxtran_pxgemr2d(lib, dtype, op, host_pointers):
+    from cosma_b200.distributed import init_comm
+    comm = init_comm()
+    grid = costa.Grid(comm, "R", 1, 1)
+    for case in TRAN_CASES:
+        assert _pxtran_case(comm, grid, grid, case, dtype, op, 1, 1, "R", "R", host_pointers, None), case
+    grid.destroy(); comm.destroy()
+
+
 # ---- multi-GPU ------------------------------------------------------------------------------------------------------
 
 def _free_port():
@@ -273,6 +327,13 @@ def _worker(rank, world, port, nprow, npcol, q):
                 for case in PX_CASES:
                     ok.append(_pxgemm_case(comm, grid, case, dtype, nprow, npcol, order, host, gather))
         grid.destroy()
+    # (3) p?tran / p?tranu / p?tranc and p?gemr2d (between a row-major and a column-major numbering of the same grid)
+    gr, gc2 = costa.Grid(comm, "R", nprow, npcol), costa.Grid(comm, "C", nprow, npcol)
+    for dtype, op in (("d", "T"), ("z", "C"), ("c", "T"), ("s", "N"), ("z", "N")):
+        for host in (False, True):
+            for case in TRAN_CASES:
+                ok.append(_pxtran_case(comm, gr, gc2 if op == "N" else gr, case, dtype, op, nprow, npcol, "R", "C" if op == "N" else "R", host, gather))
+    gr.destroy(); gc2.destroy()
     t = torch.tensor([1 if all(ok) else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
