@@ -120,12 +120,14 @@ def reference_arm(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libcosma_ref.so was not built (no /root/reference at build time)"}))
         return 0
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    R = orc.ref()
-    R.ref_set_blas_threads(ctypes.c_int(cores))
     # bounded sample: same m, n; k cut so one step is ~2 TFLOP of CPU work (a few seconds on 16 cores)
     ks = min(k, max(256, int(2.2e12 / (2.0 * m * n)) // 256 * 256))
     reps = args.warmup + args.steps
+    if args.gpus > 1 and os.path.exists(orc.REF_MINIAPP):
+        return reference_arm_ranks(args, name, m, n, k, ks, reps, cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    R = orc.ref()
+    R.ref_set_blas_threads(ctypes.c_int(cores))
     times = (ctypes.c_double * reps)()
     cs = ctypes.c_double()
     rc = R.ref_multiply_time_d(ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(ks), ctypes.c_int(reps), times, ctypes.byref(cs))
@@ -141,6 +143,47 @@ def reference_arm(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "m": m, "n": n, "k": k, "sample": sample},
             "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def reference_arm_ranks(args, name, m, n, k, ks, reps, cores):
+    """N > 1: the UNMODIFIED reference miniapp (miniapp/cosma_miniapp.cpp built into oracle/_ref/cosma_miniapp_ref) on N ranks
+    -- one per GPU of our arm -- started by oracle/minirun.py over the minimpi stand-in (processes + unix sockets), with
+    cores/N OpenBLAS threads each: the reference's own distributed CPU path (Strategy -> Mapper -> allgather / reduce ->
+    OpenBLAS dgemm) on the same bounded sample as the N = 1 arm."""
+    from oracle import oracle as orc
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from minirun import launch
+    R = args.gpus
+    threads = max(1, cores // R)
+    argv = [orc.REF_MINIAPP, "-m", str(m), "-n", str(n), "-k", str(ks), "-r", str(reps)]
+    code, outs = launch(R, argv, threads=threads, stdout=subprocess.PIPE, timeout=1500)
+    text = outs[0].decode() if outs else ""
+    times = []
+    for ln in text.splitlines():
+        if ln.startswith("COSMA TIMES [ms] ="):
+            times = [float(x) for x in ln.split("=")[1].split()]
+    if code != 0 or not times:
+        print(json.dumps({"impl": "reference", "unavailable": "reference miniapp on %d minimpi ranks failed (exit %s)" % (R, code)}))
+        return 0
+    steps = []
+    for ln in text.splitlines():
+        if ln.startswith("parallel") or ln.startswith("sequential"):
+            steps.append(ln.strip())
+    steps = steps[:max(1, len(steps) // max(1, text.count("Divisions strategy")))]  # printed once per repetition block
+    timed = sorted(times)[:args.steps]  # the miniapp reports its repetitions sorted: keep the K fastest of W + K
+    ms = sum(timed) / len(timed)
+    tf = 2.0 * m * n * ks / (ms * 1e-3) * 1e-12
+    sample = ("reference cosma_miniapp on %d minimpi ranks x %d OpenBLAS 0.3.30 threads, m=%d n=%d k=%d (k cut from %d), strategy [%s], "
+              "mean of the %d fastest of %d repetitions" % (R, threads, m, n, ks, k, "; ".join(steps), len(timed), reps))
+    line = {"impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "m": m, "n": n, "k": k, "sample": sample},
+            "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": threads * R, "kind": "reference", "sample": sample},
             "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
