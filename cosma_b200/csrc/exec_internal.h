@@ -42,7 +42,15 @@ struct Plan {
     char* owned[3] = {nullptr, nullptr, nullptr};
 };
 
-int plan_run(Plan& plan, const double* alpha, const double* beta, void* A, void* B, void* C, cudaStream_t stream);
+// host copies of the local matrices for the one GEMM of a schedule that can stream them (multiply_exec.cu)
+struct HostOperands {
+    const void* A = nullptr;
+    const void* B = nullptr;
+    const void* C_in = nullptr;
+    void* C_out = nullptr;
+};
+int plan_run(Plan& plan, const double* alpha, const double* beta, void* A, void* B, void* C, cudaStream_t stream,
+             const HostOperands* host = nullptr);
 
 // costa::transform on the device: pack kernel -> grouped ncclSend/ncclRecv -> unpack kernel
 struct TransformPlan {

@@ -6,6 +6,7 @@
 #include "exec_internal.h"
 #include "gemm_f64_sm100.h"
 #include "gemm_tf32x3_sm100.h"
+#include "host_stream.h"
 
 #include <cstring>
 
@@ -127,7 +128,8 @@ int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, char* arena, const
 
 }  // namespace
 
-int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void* B_, void* C_, cudaStream_t stream) {
+int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void* B_, void* C_, cudaStream_t stream,
+             const HostOperands* host) {
     const int E = plan.elem_reals;
     const int64_t EB = plan.elem_bytes();
     char* A = static_cast<char*>(A_);
@@ -144,7 +146,6 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
             plan.ev.push_back(e);
         }
     }
-    const float alpha_f[2] = {static_cast<float>(alpha[0]), E == 2 ? static_cast<float>(alpha[1]) : 0.0f};
     size_t gi = 0;
     for (const auto& op : plan.schedule.ops()) {
         int st = COSMA_B200_OK;
@@ -153,34 +154,25 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
                 double b[2] = {0.0, 0.0};
                 if (op.beta == cosma::BetaMode::ONE) b[0] = 1.0;
                 else if (op.beta == cosma::BetaMode::USER) { b[0] = beta[0]; b[1] = E == 2 ? beta[1] : 0.0; }
-                const float b_f[2] = {static_cast<float>(b[0]), static_cast<float>(b[1])};
-                int path = 0;
                 if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * gi], stream));
                 const int64_t lda = std::max(op.m, 1), ldb = std::max(op.k, 1), ldc = std::max(op.m, 1);
-                void* a = A + op.a_off * EB;
-                void* bp = B + op.b_off * EB;
-                void* c = C + op.c_off * EB;
-                switch (plan.dtype) {
-                    case 'd':
-                        st = dgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha[0], static_cast<double*>(a), lda, static_cast<double*>(bp), ldb, b[0],
-                                         static_cast<double*>(c), ldc, &path);
-                        break;
-                    case 'z':
-                        st = zgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha, static_cast<double*>(a), lda, static_cast<double*>(bp), ldb, b,
-                                         static_cast<double*>(c), ldc, &path);
-                        break;
-                    case 's':
-                        st = sgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha_f[0], static_cast<float*>(a), lda, static_cast<float*>(bp), ldb, b_f[0],
-                                         static_cast<float*>(c), ldc, &path);
-                        break;
-                    default:
-                        st = cgemm_sm100(stream, 'N', 'N', op.m, op.n, op.k, alpha_f, static_cast<float*>(a), lda, static_cast<float*>(bp), ldb, b_f,
-                                         static_cast<float*>(c), ldc, &path);
-                        break;
+                StreamGemmArgs g;
+                g.dtype = plan.dtype;
+                g.m = op.m; g.n = op.n; g.k = op.k;
+                g.alpha = alpha; g.beta = b;
+                g.dA = A + op.a_off * EB; g.dlda = lda;
+                g.dB = B + op.b_off * EB; g.dldb = ldb;
+                g.dC = C + op.c_off * EB; g.dldc = ldc;
+                if (host) {  // operands of this (only) GEMM still in host memory: PCIe pipelined under the kernel
+                    g.hA = host->A; g.lda = lda;
+                    g.hB = host->B; g.ldb = ldb;
+                    g.hC_in = host->C_in; g.hC_out = host->C_out; g.ldc = ldc;
                 }
+                int launches = 0;
+                st = stream_gemm(stream, g, &launches);
                 if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * gi + 1], stream));
                 ++gi;
-                if (path) ++plan.last_launches;
+                plan.last_launches += launches;
                 break;
             }
             case cosma::OpKind::ALLGATHER:
@@ -346,7 +338,7 @@ int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, voi
         set_last_error("plan was created without a communicator (plan-only); cannot execute collectives");
         return COSMA_B200_INVALID_ARG;
     }
-    return cosma_b200::plan_run(*p, alpha, beta, A, B, C, static_cast<cudaStream_t>(stream));
+    return cosma_b200::plan_run(*p, alpha, beta, A, B, C, static_cast<cudaStream_t>(stream), nullptr);
 }
 
 /* Host-pointer variant: local A, B (and C when beta != 0) are uploaded from (pinned) host memory into arenas owned by
@@ -369,17 +361,47 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
             }
         }
     const bool beta_zero = beta[0] == 0.0 && (p->elem_reals == 1 || beta[1] == 0.0);
+    // A schedule with ONE base-case GEMM that reads a local matrix as the caller holds it (no allgather of that matrix
+    // before it) / leaves local C as the caller wants it (no reduce after it) streams that matrix over PCIe under the
+    // kernel instead of copying it up front (host_gemm.cu): P = 1, and the un-gathered operands of P > 1 strategies
+    // (pk2 at P = 2: A and B; pn2,pk2 at P = 4: B; pk8 of the large-K config: A and B).
+    const cosma::ScheduleOp* gemm_op = nullptr;
+    int n_gemm = 0;
+    bool gathered[3] = {false, false, false};
+    for (const auto& op : p->schedule.ops()) {
+        if (op.kind == cosma::OpKind::GEMM) { gemm_op = &op; ++n_gemm; }
+        else gathered[op.matrix] = true;
+    }
+    cosma_b200::HostOperands hs;
+    bool streamed[3] = {false, false, false};
+    if (n_gemm == 1) {
+        const auto& g = *gemm_op;
+        const int64_t need[3] = {int64_t(g.m) * g.k, int64_t(g.k) * g.n, int64_t(g.m) * g.n};
+        const int64_t off[3] = {g.a_off, g.b_off, g.c_off};
+        for (int x = 0; x < 3; ++x)
+            streamed[x] = !gathered[x] && off[x] == 0 && need[x] == p->schedule.initial_elements(x) && need[x] > 0;
+        if (streamed[0]) hs.A = A;
+        if (streamed[1]) hs.B = B;
+        if (streamed[2]) { hs.C_in = C; hs.C_out = C; }
+    }
     const void* host_in[3] = {A, B, C};
     for (int x = 0; x < 3; ++x) {
-        if (x == 2 && beta_zero) continue;
+        if (streamed[x] || (x == 2 && beta_zero)) continue;
         const size_t bytes = p->schedule.initial_elements(x) * es;
         if (bytes && cudaMemcpyAsync(p->owned[x], host_in[x], bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
             return COSMA_B200_CUDA_ERROR;
     }
-    int rc = cosma_b200_multiply(plan, alpha, beta, p->owned[0], p->owned[1], p->owned[2], stream);
+    bool needs_comm = false;
+    for (const auto& op : p->schedule.ops()) needs_comm |= op.kind != cosma::OpKind::GEMM;
+    if (needs_comm && p->ring_comms.empty()) {
+        set_last_error("plan was created without a communicator (plan-only); cannot execute collectives");
+        return COSMA_B200_INVALID_ARG;
+    }
+    const bool any = streamed[0] || streamed[1] || streamed[2];
+    int rc = cosma_b200::plan_run(*p, alpha, beta, p->owned[0], p->owned[1], p->owned[2], st, any ? &hs : nullptr);
     if (rc != COSMA_B200_OK) return rc;
     const size_t cbytes = p->schedule.initial_elements(2) * es;
-    if (cbytes && cudaMemcpyAsync(C, p->owned[2], cbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+    if (!streamed[2] && cbytes && cudaMemcpyAsync(C, p->owned[2], cbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
     return COSMA_B200_OK;
 }
 

@@ -46,3 +46,21 @@ def local_multiply(A, B, C, m, n, k, alpha, beta, stream=None):
     dt = {torch.float64: "d", torch.complex128: "z", torch.float32: "s", torch.complex64: "c"}[C.dtype]
     gemm_raw(dt, "N", "N", m, n, k, alpha, A.data_ptr(), max(m, 1), B.data_ptr(), max(k, 1), beta, C.data_ptr(),
              max(m, 1), stream)
+
+
+def gemm_host(dtype, m, n, k, alpha, hA, lda, hB, ldb, beta, hC, ldc, stream=None):
+    """cosma_b200_{d,z}gemm_host: 'N','N' GEMM on HOST (pinned) torch tensors, PCIe pipelined under the kernel -- the
+    calling convention of the reference's GPU base case (gpu::gemm with host pointers, local_multiply.cpp:219-269)."""
+    lib = _lib.load()
+    fn = getattr(lib, "cosma_b200_%sgemm_host" % dtype)
+    fn.argtypes = [ctypes.c_void_p] + [ctypes.c_int64] * 3 + [ctypes.c_void_p] * 2 + [ctypes.c_int64] + \
+        [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    fn.restype = ctypes.c_int
+    if dtype == "d":
+        al = (ctypes.c_double * 1)(float(alpha)); be = (ctypes.c_double * 1)(float(beta))
+    else:
+        al = (ctypes.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+        be = (ctypes.c_double * 2)(complex(beta).real, complex(beta).imag)
+    st = fn(_stream_ptr(stream), m, n, k, al, hA.data_ptr(), lda, hB.data_ptr(), ldb, be, hC.data_ptr(), ldc)
+    _lib.check(st, "cosma_b200_%sgemm_host" % dtype)
+    return lib.cosma_b200_last_launch_count()

@@ -147,3 +147,43 @@ def test_dgemm_full_size_properties():
     # linearity: alpha = 2, beta = 1 on top of the result gives 3x
     gemm.gemm_raw("d", "N", "N", n, n, n, 2.0, A.data_ptr(), n, B.data_ptr(), n, 1.0, C.data_ptr(), n)
     assert torch.equal(C.view(n, n).sum(dim=1), 3 * col_check)
+
+
+@pytest.mark.parametrize("dtype,m,n,k,lda_pad,beta", [
+    ("d", 1700, 3072 + 2048 + 1700, 40, 0, 0.0), ("d", 1601, 3072 + 100, 33, 3, 1.0), ("d", 300, 200, 100, 0, 1.0),
+    ("z", 900, 1536 + 2048 + 1100, 24, 0, 0.0), ("z", 801, 1600, 17, 1, 1.0),
+])
+def test_gemm_host_streamed(oracle, dtype, m, n, k, lda_pad, beta):
+    """cosma_b200_{d,z}gemm_host (host operands; A in row chunks under the first panel, B and C in column panels):
+    bit-exact on integer-valued inputs against the oracle, padding of host C untouched, beta == 0 never reads C."""
+    from cosma_b200 import gemm
+    rng = np.random.default_rng(5)
+    cplx = dtype == "z"
+    npdt = np.complex128 if cplx else np.float64
+    lda, ldb, ldc = m + lda_pad, k + lda_pad, m + lda_pad
+
+    def fill(cnt):
+        v = rng.integers(0, 10, size=cnt).astype(np.float64)
+        if cplx:
+            v = v + 1j * rng.integers(0, 10, size=cnt)
+        return v.astype(npdt)
+    A, B, C = fill(lda * k), fill(ldb * n), fill(ldc * n)
+    want = oracle.gemm("N", "N", m, n, k, 1.0, A, lda, B, ldb, beta, C.copy(), ldc)
+    hA, hB = torch.from_numpy(A).pin_memory(), torch.from_numpy(B).pin_memory()
+    C0 = C.copy()
+    if beta == 0.0:
+        C0.reshape(n, ldc)[:, :m] = np.nan
+    for _ in range(2):
+        hC = torch.from_numpy(C0.copy()).pin_memory()
+        launches = gemm.gemm_host(dtype, m, n, k, 1.0, hA, lda, hB, ldb, beta, hC, ldc)
+        torch.cuda.synchronize()
+        got = hC.numpy().reshape(n, ldc)
+        assert np.array_equal(got[:, :m], want.reshape(n, ldc)[:, :m])
+        assert np.array_equal(got[:, m:], C.reshape(n, ldc)[:, m:])
+    assert launches >= 1
+    _lib_release()
+
+
+def _lib_release():
+    from cosma_b200 import _lib
+    _lib.load().cosma_b200_release_workspace()

@@ -85,6 +85,34 @@ def test_single_gpu_host_entry_point(oracle):
     pl.destroy()
 
 
+@pytest.mark.parametrize("dtype", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_single_gpu_host_entry_point_streamed(oracle, dtype, beta):
+    """P = 1, one GEMM: A in row chunks under a wide first panel, B / C in column panels (host_gemm.cu). Sizes span
+    several row chunks (768) and panels (first 3072 / 1536 / 5632 / 3072 for d / z / s / c, then 2048, thin tail)."""
+    from cosma_b200.distributed import MultiplyPlan
+    m, k = 1700, 48
+    n = {"d": 3072 + 2048 + 1700, "z": 1536 + 2048 + 1100, "s": 5632 + 2048 + 300, "c": 3072 + 2048 + 2048 + 1600}[dtype]
+    Ag, Bg, Cg = _globals(m, n, k, dtype)
+    pl = MultiplyPlan(None, m, n, k, "", dtype, rank=0, nranks=1)
+    tdt = {"d": torch.float64, "z": torch.complex128, "s": torch.float32, "c": torch.complex64}[dtype]
+    hs = [torch.from_numpy(np.ascontiguousarray(x.T).reshape(-1).copy()).to(tdt).pin_memory() for x in (Ag, Bg, Cg)]
+    if beta == 0.0:
+        hs[2].fill_(float("nan"))
+    for _ in range(2):  # twice: buffers and events are reused
+        if beta != 0.0:
+            hs[2].copy_(torch.from_numpy(np.ascontiguousarray(Cg.T).reshape(-1)))
+        pl.multiply_host(hs[0], hs[1], hs[2], 1.0, beta)
+        torch.cuda.synchronize()
+    got = hs[2].numpy().reshape(n, m).T
+    wide = np.complex128 if dtype in "zc" else np.float64
+    want = (Ag.astype(wide) @ Bg.astype(wide) + beta * Cg.astype(wide)).astype(Ag.dtype)
+    assert np.array_equal(got, want)
+    if dtype == "d":  # and against the oracle proper
+        assert np.array_equal(got, _dense_oracle(oracle, Ag, Bg, Cg, 1.0, beta))
+    pl.destroy()
+
+
 # ---- multi-GPU: one process per GPU, NCCL ---------------------------------------------------------------------------
 
 def _free_port():
@@ -101,7 +129,8 @@ def _worker(rank, world, port, cases, q):
     from cosma_b200.distributed import init_comm, MultiplyPlan, fill_local_from_global, gather_local_to_global
     comm = init_comm()
     results = []
-    for (m, n, k, steps, dtype, alpha, beta) in cases:
+    for case in cases:
+        (m, n, k, steps, dtype, alpha, beta), via_host = case[:7], len(case) > 7 and case[7] == "host"
         Ag, Bg, Cg = _globals(m, n, k, dtype)
         pl = MultiplyPlan(comm, m, n, k, steps, dtype)
         if not pl.idle:
@@ -117,7 +146,14 @@ def _worker(rank, world, port, cases, q):
                 pl.C.local.copy_(torch.from_numpy(host))
                 if beta == 0.0:
                     pl.C.local.fill_(float("nan"))
-            pl.multiply(alpha, beta)
+            if via_host and not pl.idle:
+                # host-pointer entry point: pinned local matrices in, local C out (un-gathered operands are streamed)
+                hs = [t.local.cpu().pin_memory() for t in (pl.A, pl.B, pl.C)]
+                pl.multiply_host(hs[0], hs[1], hs[2], alpha, beta)
+                torch.cuda.synchronize()
+                pl.C.local.copy_(hs[2])
+            else:
+                pl.multiply(alpha, beta)
         torch.cuda.synchronize()
         # gather the local C buffers on rank 0 through torch.distributed (test plumbing only)
         tdt = {"d": torch.float64, "z": torch.complex128, "s": torch.float32, "c": torch.complex64}[dtype]
@@ -172,6 +208,12 @@ def test_two_gpus(lib):
         (256, 256, 256, "pk2", "z", 1.0 - 0.5j, 0.5j),
         (512, 384, 256, "pk2", "s", 1.0, 1.0),              # single precision: 3xTF32 tcgen05 base case, float NCCL reduce
         (300, 260, 220, "sm2,pn2,sk3", "c", 2.0, 1.0),
+        # cosma_b200_multiply_host: A and B streamed under the GEMM (pk2); only B (pn2) / only A (pm2) with C streamed out
+        (1700, 7000, 96, "pk2", "d", 1.0, 0.0, "host"),
+        (1700, 7000, 96, "pk2", "d", 1.0, 1.0, "host"),
+        (1000, 9000, 64, "pn2", "d", 1.0, 1.0, "host"),
+        (1800, 4000, 64, "pm2", "z", 1.0, 0.0, "host"),
+        (300, 260, 220, "sm2,pn2,sk3", "d", 2.0, 1.0, "host"),  # several GEMMs: plain up-front copies
     ])
 
 
