@@ -255,6 +255,14 @@ bool is_host_pointer(const void* p) {
     return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeUnregistered;
 }
 
+// D2H of a staged local array: only the rank's local rows of every column (the padding rows between the local row count and
+// lld belong to the caller and were possibly never uploaded)
+cudaError_t download_local(void* host, const void* dev, int lld, int loc_rows, int loc_cols, int eb, cudaStream_t stream) {
+    if (loc_rows <= 0 || loc_cols <= 0) return cudaSuccess;
+    return cudaMemcpy2DAsync(host, static_cast<size_t>(lld) * eb, dev, static_cast<size_t>(lld) * eb, static_cast<size_t>(loc_rows) * eb,
+                             loc_cols, cudaMemcpyDeviceToHost, stream);
+}
+
 }  // namespace
 }  // namespace cosma_b200
 
@@ -416,7 +424,9 @@ static int xpgemm(void* grid, char dtype, char transa, char transb, int m, int n
             rc = layout_multiply(g->comm, dtype, ta, tb, m, n, k, a2, b2, LA, LB, LC, "", stream, nullptr);
         }
         if (rc != COSMA_B200_OK) return rc;
-        if (staged[2]) COSMA_B200_CUDA_TRY(cudaMemcpyAsync(c, dev[2], local_bytes[2], cudaMemcpyDeviceToHost, stream));
+        if (staged[2])
+            COSMA_B200_CUDA_TRY(download_local(c, dev[2], descc[8], costa::numroc(descc[2], descc[4], myrow, descc[6], g->nprow),
+                                               costa::numroc(descc[3], descc[5], mycol, descc[7], g->npcol), eb, stream));
         return COSMA_B200_OK;
     } catch (const std::exception& e) {
         set_last_error(e.what());
@@ -530,7 +540,12 @@ static int xptransform(Grid* ga, Grid* gc, char dtype, char op, int m, int n, co
         int rc = transform_plan_run(*entry->plan, stream);
         if (rc != COSMA_B200_OK) return rc;
         gc->last_launches = entry->plan->last_launches;
-        if (staged[1]) COSMA_B200_CUDA_TRY(cudaMemcpyAsync(c, dev[1], local_bytes[1], cudaMemcpyDeviceToHost, stream));
+        if (staged[1]) {
+            int myrow = 0, mycol = 0;
+            costa::rank_to_grid(rank, gc->nprow, gc->npcol, gc->order, &myrow, &mycol);
+            COSMA_B200_CUDA_TRY(download_local(c, dev[1], descc[8], costa::numroc(descc[2], descc[4], myrow, descc[6], gc->nprow),
+                                               costa::numroc(descc[3], descc[5], mycol, descc[7], gc->npcol), eb, stream));
+        }
         return COSMA_B200_OK;
     } catch (const std::exception& e) {
         set_last_error(e.what());
