@@ -1,0 +1,7 @@
+// libcosma_prefixed_pxgemm.so: cosma_p?gemm / COSMA_P?GEMM, for callers that want both ScaLAPACK's and COSMA's p?gemm in
+// one executable (reference src/cosma/prefixed_pxgemm.cpp).
+#include <cosma/cosma_pxgemm.hpp>
+#include <cosma/prefixed_pxgemm.h>
+#define COSMA_B200_SYM(x) cosma_##x
+#define COSMA_B200_SYM_UP(x) COSMA_##x
+#include "pxgemm_symbols.inc"

@@ -64,6 +64,34 @@ int cosma_b200_zgemm_host(void* stream, int64_t m, int64_t n, int64_t k, const d
                                      &g_last_launches);
 }
 int cosma_b200_last_launch_count(void) { return g_last_launches; }
+
+static int cuda_status(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return COSMA_B200_OK;
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? COSMA_B200_OUT_OF_MEMORY : COSMA_B200_CUDA_ERROR;
+}
+int cosma_b200_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return COSMA_B200_INVALID_ARG;
+    *ptr = nullptr;
+    if (bytes == 0) return COSMA_B200_OK;
+    return cuda_status(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable), "cudaHostAlloc");
+}
+int cosma_b200_host_free(void* ptr) { return ptr ? cuda_status(cudaFreeHost(ptr), "cudaFreeHost") : COSMA_B200_OK; }
+int cosma_b200_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return COSMA_B200_OK;
+    return cuda_status(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable), "cudaHostRegister");
+}
+int cosma_b200_host_unregister(void* ptr) { return ptr ? cuda_status(cudaHostUnregister(ptr), "cudaHostUnregister") : COSMA_B200_OK; }
+int cosma_b200_device_count(int* count) {
+    if (!count) return COSMA_B200_INVALID_ARG;
+    *count = 0;
+    return cuda_status(cudaGetDeviceCount(count), "cudaGetDeviceCount");
+}
+int cosma_b200_set_device(int device) { return cuda_status(cudaSetDevice(device), "cudaSetDevice"); }
+int cosma_b200_stream_synchronize(void* stream) {
+    return cuda_status(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
+}
 void cosma_b200_release_workspace(void) { cosma_b200::release_host_gemm_workspace(); }
 
 }  // extern "C"

@@ -3,9 +3,10 @@
 #include "../../include/cosma_b200.h"
 #include "nccl_dyn.h"
 #include "relayout_sm100.h"
+#include "host_mirror.h"
 
 #include <cosma/schedule.hpp>
-#include <costa/transform.hpp>
+#include <costa/transform_plan.hpp>
 
 #include <map>
 #include <memory>
@@ -63,6 +64,7 @@ struct TransformPlan {
     RelayoutBatch stage2;  // unpack pieces
     int last_launches = 0;
     bool materialised = false;  // device buffers allocated and piece lists uploaded
+    HostMirror mirror;          // device copies of the layout blocks that live in host memory (none: inactive)
     ~TransformPlan();
 };
 // Builds the device plan (allocates buffers, uploads piece lists). comm may be null (planning only / single rank).

@@ -1,4 +1,4 @@
-#include <costa/layout.hpp>
+#include <costa/erased_layout.hpp>
 
 #include <stdexcept>
 
@@ -20,30 +20,30 @@ void assigned_grid2D::reorder_ranks(const std::vector<int>& perm) {
     for (auto& o : owners) o = perm[o];
 }
 
-grid_layout custom_layout(int rowblocks, int colblocks, const int* rowsplit, const int* colsplit, const int* owners,
+erased_layout erased_custom_layout(int rowblocks, int colblocks, const int* rowsplit, const int* colsplit, const int* owners,
                           int nlocalblocks, const int* block_rows, const int* block_cols, void* const* block_data,
                           const std::int64_t* block_ld, char ordering) {
-    if (rowblocks < 0 || colblocks < 0 || nlocalblocks < 0) throw std::runtime_error("custom_layout: negative block count");
-    if (ordering != 'C' && ordering != 'R') throw std::runtime_error("custom_layout: ordering must be 'C' or 'R'");
-    grid_layout l;
+    if (rowblocks < 0 || colblocks < 0 || nlocalblocks < 0) throw std::runtime_error("erased_custom_layout: negative block count");
+    if (ordering != 'C' && ordering != 'R') throw std::runtime_error("erased_custom_layout: ordering must be 'C' or 'R'");
+    erased_layout l;
     l.ordering = ordering;
     l.grid.grid.rows_split.assign(rowsplit, rowsplit + rowblocks + 1);
     l.grid.grid.cols_split.assign(colsplit, colsplit + colblocks + 1);
     for (int i = 0; i < rowblocks; ++i)
-        if (rowsplit[i + 1] < rowsplit[i]) throw std::runtime_error("custom_layout: rowsplit must be non-decreasing");
+        if (rowsplit[i + 1] < rowsplit[i]) throw std::runtime_error("erased_custom_layout: rowsplit must be non-decreasing");
     for (int j = 0; j < colblocks; ++j)
-        if (colsplit[j + 1] < colsplit[j]) throw std::runtime_error("custom_layout: colsplit must be non-decreasing");
+        if (colsplit[j + 1] < colsplit[j]) throw std::runtime_error("erased_custom_layout: colsplit must be non-decreasing");
     l.grid.owners.assign(owners, owners + static_cast<size_t>(rowblocks) * colblocks);
     int max_owner = 0;
     for (int o : l.grid.owners) {
-        if (o < 0) throw std::runtime_error("custom_layout: negative owner");
+        if (o < 0) throw std::runtime_error("erased_custom_layout: negative owner");
         if (o > max_owner) max_owner = o;
     }
     l.grid.n_ranks = max_owner + 1;
     l.blocks.resize(nlocalblocks);
     for (int b = 0; b < nlocalblocks; ++b) {
         if (block_rows[b] < 0 || block_rows[b] >= rowblocks || block_cols[b] < 0 || block_cols[b] >= colblocks)
-            throw std::runtime_error("custom_layout: local block coordinates outside the grid");
+            throw std::runtime_error("erased_custom_layout: local block coordinates outside the grid");
         l.blocks[b] = local_block{block_rows[b], block_cols[b], block_data[b], block_ld[b]};
     }
     return l;
@@ -81,15 +81,15 @@ void rank_to_grid(int rank, int nprow, int npcol, char order, int* prow, int* pc
     }
 }
 
-grid_layout get_scalapack_layout(int lld, int mat_rows, int mat_cols, int ia, int ja, int sub_m, int sub_n, int mb, int nb,
+erased_layout erased_scalapack_layout(int lld, int mat_rows, int mat_cols, int ia, int ja, int sub_m, int sub_n, int mb, int nb,
                                  int nprow, int npcol, char grid_order, int rsrc, int csrc, void* ptr, int elem_bytes,
                                  char data_ordering, int rank) {
     (void)mat_rows;
     (void)mat_cols;
-    if (ia < 1 || ja < 1) throw std::runtime_error("get_scalapack_layout: ia, ja are 1-based");
-    if (mb < 1 || nb < 1 || nprow < 1 || npcol < 1) throw std::runtime_error("get_scalapack_layout: bad block or grid size");
+    if (ia < 1 || ja < 1) throw std::runtime_error("erased_scalapack_layout: ia, ja are 1-based");
+    if (mb < 1 || nb < 1 || nprow < 1 || npcol < 1) throw std::runtime_error("erased_scalapack_layout: bad block or grid size");
     const int r0 = ia - 1, c0 = ja - 1;
-    grid_layout l;
+    erased_layout l;
     l.ordering = data_ordering;
     l.grid.n_ranks = nprow * npcol;
     l.grid.grid.rows_split = line_split(r0, r0 + sub_m, mb);

@@ -1,4 +1,4 @@
-#include <costa/transform.hpp>
+#include <costa/transform_plan.hpp>
 
 #include <algorithm>
 #include <map>
@@ -33,7 +33,7 @@ std::vector<int> covering_block(const std::vector<int>& lines, const std::vector
     return out;
 }
 
-std::map<std::pair<int, int>, const local_block*> index_blocks(const grid_layout& l) {
+std::map<std::pair<int, int>, const local_block*> index_blocks(const erased_layout& l) {
     std::map<std::pair<int, int>, const local_block*> m;
     for (const auto& b : l.blocks) m[{b.bi, b.bj}] = &b;
     return m;
@@ -56,8 +56,8 @@ transform_plan plan_transform(const std::vector<transform_spec>& specs, int rank
     for (size_t si = 0; si < specs.size(); ++si) {
         const transform_spec& spec = specs[si];
         if (!spec.from || !spec.to) throw std::runtime_error("plan_transform: null layout");
-        const grid_layout& F = *spec.from;
-        const grid_layout& T = *spec.to;
+        const erased_layout& F = *spec.from;
+        const erased_layout& T = *spec.to;
         const char op = spec.op == 'n' ? 'N' : spec.op == 't' ? 'T' : spec.op == 'c' ? 'C' : spec.op;
         if (op != 'N' && op != 'T' && op != 'C') throw std::runtime_error("plan_transform: op must be N, T or C");
         const bool tr = op != 'N';

@@ -11,19 +11,19 @@
 // its context, context.cpp:80-125, and re-derives the COSTA messages on every call).
 #include "exec_internal.h"
 
-#include <costa/layout.hpp>
+#include <costa/erased_layout.hpp>
 
 #include <cstring>
 
 namespace cosma_b200 {
 
-costa::grid_layout layout_from_c(const cosma_b200_layout& l, char ordering, int nranks);  // transform_exec.cu
+costa::erased_layout layout_from_c(const cosma_b200_layout& l, char ordering, int nranks);  // transform_exec.cu
 
 struct LayoutMultiplyState {
     void* plan = nullptr;  // cosma_b200 multiply plan (Plan*)
     char dtype = 'd';
     char* arena[3] = {nullptr, nullptr, nullptr};
-    costa::grid_layout native[3];  // COSMA layouts of A, B, C with blocks pointing into the arenas
+    costa::erased_layout native[3];  // COSMA layouts of A, B, C with blocks pointing into the arenas
     struct Entry {
         std::string key;
         std::unique_ptr<TransformPlan> in, out;
@@ -79,7 +79,7 @@ struct Grid {
 
 void append(std::string& key, const void* p, size_t n) { key.append(static_cast<const char*>(p), n); }
 
-void append_layout(std::string& key, const costa::grid_layout& l) {
+void append_layout(std::string& key, const costa::erased_layout& l) {
     append(key, l.grid.grid.rows_split.data(), l.grid.grid.rows_split.size() * sizeof(int));
     append(key, l.grid.grid.cols_split.data(), l.grid.grid.cols_split.size() * sizeof(int));
     append(key, l.grid.owners.data(), l.grid.owners.size() * sizeof(int));
@@ -96,15 +96,27 @@ void append_layout(std::string& key, const costa::grid_layout& l) {
 bool is_zero(const double* v, bool cplx) { return v[0] == 0.0 && (!cplx || v[1] == 0.0); }
 
 // C = beta * C on the caller's layout (grid_layout::scale_by, reference grid_layout.hpp:55-63); beta == 0 stores zeros
-int scale_layout(char dtype, const costa::grid_layout& C, const double* beta, cudaStream_t stream) {
+int scale_layout(char dtype, const costa::erased_layout& C, const double* beta, cudaStream_t stream) {
     const bool cplx = dtype == 'c' || dtype == 'z';
     if (beta[0] == 1.0 && (!cplx || beta[1] == 0.0)) return COSMA_B200_OK;
     std::vector<costa::piece> ps;
+    const int eb = dtype_bytes(dtype);
+    const bool beta_zero = is_zero(beta, cplx);
+    HostMirror mirror;  // blocks in host memory are scaled through a device mirror
+    for (const auto& b : C.blocks) {
+        const size_t rows = C.grid.grid.rows_split[b.bi + 1] - C.grid.grid.rows_split[b.bi];
+        const size_t cols = C.grid.grid.cols_split[b.bj + 1] - C.grid.grid.cols_split[b.bj];
+        const size_t run = C.ordering == 'R' ? cols : rows, runs = C.ordering == 'R' ? rows : cols;
+        mirror.add(b.data, static_cast<size_t>(std::max<std::int64_t>(b.ld, static_cast<std::int64_t>(run))) * eb, run * eb, runs, true, !beta_zero);
+    }
+    int ms = mirror.build();
+    if (ms != COSMA_B200_OK) return ms;
+    if (mirror.active() && (ms = mirror.upload(stream)) != COSMA_B200_OK) return ms;
     for (const auto& b : C.blocks) {
         costa::piece p;
         p.n_rows = C.grid.grid.rows_split[b.bi + 1] - C.grid.grid.rows_split[b.bi];
         p.n_cols = C.grid.grid.cols_split[b.bj + 1] - C.grid.grid.cols_split[b.bj];
-        p.src = b.data; p.dst = b.data;
+        p.src = mirror.translate(b.data); p.dst = mirror.translate(b.data);
         p.src_ld = p.dst_ld = b.ld;
         p.src_ordering = p.dst_ordering = C.ordering;
         p.scale_only = true;
@@ -119,7 +131,8 @@ int scale_layout(char dtype, const costa::grid_layout& C, const double* beta, cu
     relayout_normalise(ps, nullptr, nullptr, dtype_bytes(dtype), specs, list);
     int st = relayout_upload(list, batch);
     if (st == COSMA_B200_OK) st = relayout_launch(batch, dtype, stream);
-    if (!batch.empty()) cudaStreamSynchronize(stream);
+    if (st == COSMA_B200_OK && mirror.active()) st = mirror.download(stream);
+    if (!batch.empty() || mirror.active()) cudaStreamSynchronize(stream);
     relayout_free(batch);
     return st;
 }
@@ -147,7 +160,7 @@ int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, Layou
         // the COSMA layout as a COSTA grid (reference Mapper::get_layout_grid, mapper.cpp:369-414, and
         // CosmaMatrix::get_grid_layout, matrix.cpp:393-429: one column-major block per Mapper block, ld = rows)
         const cosma::Mapper& mapper = plan->schedule.mapper(x);
-        costa::grid_layout& L = st->native[x];
+        costa::erased_layout& L = st->native[x];
         L.ordering = 'C';
         L.grid.grid.rows_split = mapper.row_split();
         L.grid.grid.cols_split = mapper.col_split();
@@ -176,7 +189,7 @@ int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, Layou
 }
 
 int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, const double* alpha, const double* beta,
-                    const costa::grid_layout& A, const costa::grid_layout& B, const costa::grid_layout& C, const char* steps,
+                    const costa::erased_layout& A, const costa::erased_layout& B, const costa::erased_layout& C, const char* steps,
                     cudaStream_t stream, int* launches) {
     const bool cplx = dtype == 'c' || dtype == 'z';
     if (launches) *launches = 0;
@@ -246,14 +259,6 @@ int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, 
     return COSMA_B200_OK;
 }
 
-bool is_host_pointer(const void* p) {
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
-        cudaGetLastError();
-        return true;
-    }
-    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeUnregistered;
-}
 
 // D2H of a staged local array: only the rank's local rows of every column (the padding rows between the local row count and
 // lld belong to the caller and were possibly never uploaded)
@@ -277,7 +282,7 @@ static int xmultiply_using_layout(void* comm, char dtype, const char* transa, co
     if (!c || !transa || !transb || !alpha || !beta || !A || !B || !C) return COSMA_B200_INVALID_ARG;
     try {
         const char ta = std::toupper(*transa), tb = std::toupper(*transb);
-        const costa::grid_layout LA = layout_from_c(*A, 'C', c->size), LB = layout_from_c(*B, 'C', c->size),
+        const costa::erased_layout LA = layout_from_c(*A, 'C', c->size), LB = layout_from_c(*B, 'C', c->size),
                                  LC = layout_from_c(*C, 'C', c->size);
         const int m = LC.num_rows(), n = LC.num_cols();
         const int k = ta == 'N' ? LA.num_cols() : LA.num_rows();
@@ -408,17 +413,17 @@ static int xpgemm(void* grid, char dtype, char transa, char transb, int m, int n
         }
 
         auto layout_of = [&](int x, int i0, int j0, int sm, int sn) {
-            return costa::get_scalapack_layout(desc[x][8], desc[x][2], desc[x][3], i0, j0, sm, sn, desc[x][4], desc[x][5], g->nprow, g->npcol,
+            return costa::erased_scalapack_layout(desc[x][8], desc[x][2], desc[x][3], i0, j0, sm, sn, desc[x][4], desc[x][5], g->nprow, g->npcol,
                                                g->order, desc[x][6], desc[x][7], dev[x], eb, 'C', in_grid ? rank : -1);
         };
         const double a2[2] = {alpha[0], cplx ? alpha[1] : 0.0}, b2[2] = {beta[0], cplx ? beta[1] : 0.0};
         int rc;
         if (scale_only) {
-            costa::grid_layout LC = layout_of(2, ic, jc, m, n);
+            costa::erased_layout LC = layout_of(2, ic, jc, m, n);
             LC.grid.n_ranks = g->comm->size;
             rc = scale_layout(dtype, LC, b2, stream);
         } else {
-            costa::grid_layout LA = layout_of(0, ia, ja, a_subm, a_subn), LB = layout_of(1, ib, jb, b_subm, b_subn),
+            costa::erased_layout LA = layout_of(0, ia, ja, a_subm, a_subn), LB = layout_of(1, ib, jb, b_subm, b_subn),
                                LC = layout_of(2, ic, jc, m, n);
             LA.grid.n_ranks = LB.grid.n_ranks = LC.grid.n_ranks = g->comm->size;
             rc = layout_multiply(g->comm, dtype, ta, tb, m, n, k, a2, b2, LA, LB, LC, "", stream, nullptr);
@@ -503,9 +508,9 @@ static int xptransform(Grid* ga, Grid* gc, char dtype, char op, int m, int n, co
             if (upload) COSMA_B200_CUDA_TRY(cudaMemcpyAsync(dev[x], user[x], local_bytes[x], cudaMemcpyHostToDevice, stream));
         }
         const int a_subm = op == 'N' ? m : n, a_subn = op == 'N' ? n : m;
-        costa::grid_layout LA = costa::get_scalapack_layout(desca[8], desca[2], desca[3], ia, ja, a_subm, a_subn, desca[4], desca[5], ga->nprow,
+        costa::erased_layout LA = costa::erased_scalapack_layout(desca[8], desca[2], desca[3], ia, ja, a_subm, a_subn, desca[4], desca[5], ga->nprow,
                                                             ga->npcol, ga->order, desca[6], desca[7], dev[0], eb, 'C', in_grid[0] ? rank : -1);
-        costa::grid_layout LC = costa::get_scalapack_layout(descc[8], descc[2], descc[3], ic, jc, m, n, descc[4], descc[5], gc->nprow, gc->npcol,
+        costa::erased_layout LC = costa::erased_scalapack_layout(descc[8], descc[2], descc[3], ic, jc, m, n, descc[4], descc[5], gc->nprow, gc->npcol,
                                                             gc->order, descc[6], descc[7], dev[1], eb, 'C', in_grid[1] ? rank : -1);
         LA.grid.n_ranks = LC.grid.n_ranks = comm->size;
         std::string key;

@@ -236,8 +236,23 @@ int cosma_b200_comm_destroy(void* comm) {
     return COSMA_B200_OK;
 }
 
+static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int k, int P, const char* steps, char dtype, void** plan_out);
+
 int cosma_b200_plan_create(void* comm, int rank, int nranks, int m, int n, int k, const char* steps, char dtype,
                            void** plan_out) {
+    return plan_create_impl(comm, rank, nranks, m, n, k, /*P=*/0, steps, dtype, plan_out);
+}
+int cosma_b200_plan_create_for_strategy(void* comm, int rank, int nranks, int m, int n, int k, int P, const char* steps, char dtype,
+                                        void** plan_out) {
+    if (P < 1) {
+        set_last_error("plan_create_for_strategy: P must be >= 1");
+        return COSMA_B200_INVALID_ARG;
+    }
+    return plan_create_impl(comm, rank, nranks, m, n, k, P, steps, dtype, plan_out);
+}
+
+// P == 0: Strategy(m, n, k, nranks) completed automatically when `steps` is empty; P >= 1: exactly the caller's strategy
+static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int k, int P, const char* steps, char dtype, void** plan_out) {
     try {
         if (dtype != 'd' && dtype != 'z' && dtype != 's' && dtype != 'c') {
             set_last_error("plan dtype must be one of s, d, c, z");
@@ -245,7 +260,23 @@ int cosma_b200_plan_create(void* comm, int rank, int nranks, int m, int n, int k
         }
         Comm* c = static_cast<Comm*>(comm);
         if (c) { rank = c->rank; nranks = c->size; }
-        cosma::Strategy strategy = cosma::parse_strategy(m, n, k, nranks, steps ? steps : "");
+        if (P > nranks) {
+            set_last_error("the strategy uses more ranks than the communicator has");
+            return COSMA_B200_INVALID_ARG;
+        }
+        cosma::Strategy strategy;
+        if (P == 0) {
+            strategy = cosma::parse_strategy(m, n, k, nranks, steps ? steps : "");
+        } else {
+            const std::string st = steps ? steps : "";
+            if (st.find_first_not_of(" ,") == std::string::npos) {
+                std::vector<int> divs;
+                std::string dims, types;
+                strategy = cosma::Strategy(m, n, k, static_cast<size_t>(P), divs, dims, types);  // valid only for P == 1
+            } else {
+                strategy = cosma::parse_strategy(m, n, k, static_cast<size_t>(P), st);
+            }
+        }
         auto plan = std::make_unique<Plan>();
         plan->schedule = cosma::Schedule(strategy, rank);
         plan->dtype = dtype;

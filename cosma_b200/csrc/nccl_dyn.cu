@@ -1,5 +1,6 @@
 #include "nccl_dyn.h"
 
+#include <cstdlib>
 #include <dlfcn.h>
 #include <mutex>
 #include <string>
@@ -13,7 +14,12 @@ const NcclApi* nccl() {
     static std::once_flag once;
     std::call_once(once, [] {
         void* h = nullptr;
+        // COSMA_B200_NCCL_LIB: explicit path; otherwise whatever libnccl the process already loaded (torch's bundled one
+        // under Python) or the dynamic loader finds (the system NCCL for plain C++ / Fortran hosts)
+        if (const char* path = std::getenv("COSMA_B200_NCCL_LIB"))
+            if (*path) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            if (h) break;
             h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (h) break;
         }

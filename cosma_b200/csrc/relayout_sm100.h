@@ -1,6 +1,6 @@
 // Internal C++ interface of the batched relayout kernel (R3/R4). The public door is include/cosma_b200.h.
 #pragma once
-#include <costa/transform.hpp>
+#include <costa/transform_plan.hpp>
 
 #include <cstdint>
 #include <vector>

@@ -35,6 +35,21 @@ int transform_plan_build(Comm* comm, int rank, int nranks, char dtype, const std
         set_last_error(e.what());
         return COSMA_B200_INVALID_ARG;
     }
+    // remember where the caller's blocks are: if they turn out to be host memory when the plan first runs, they are mirrored
+    for (const auto& sp : specs) {
+        const bool reads_target = sp.beta[0] != 0.0 || sp.beta[1] != 0.0;
+        for (int side = 0; side < 2; ++side) {
+            const costa::erased_layout* L = side == 0 ? sp.from : sp.to;
+            if (!L) continue;
+            for (const auto& b : L->blocks) {
+                const size_t rows = L->grid.grid.rows_split[b.bi + 1] - L->grid.grid.rows_split[b.bi];
+                const size_t cols = L->grid.grid.cols_split[b.bj + 1] - L->grid.grid.cols_split[b.bj];
+                const size_t run = L->ordering == 'R' ? cols : rows, runs = L->ordering == 'R' ? rows : cols;
+                tp->mirror.add(b.data, static_cast<size_t>(std::max<std::int64_t>(b.ld, static_cast<std::int64_t>(run))) * eb, run * eb, runs,
+                               side == 1, reads_target);
+            }
+        }
+    }
     out = std::move(tp);
     return COSMA_B200_OK;
 }
@@ -44,7 +59,14 @@ namespace {
 int materialise(TransformPlan& tp) {
     if (tp.materialised) return COSMA_B200_OK;
     tp.materialised = true;
-    const auto& h = tp.host;
+    auto& h = tp.host;
+    int ms = tp.mirror.build();
+    if (ms != COSMA_B200_OK) return ms;
+    if (tp.mirror.active()) {  // host-resident blocks: the pieces address their device mirrors from now on
+        for (auto& p : h.pack) p.src = tp.mirror.translate(p.src);
+        for (auto& p : h.local) { p.src = tp.mirror.translate(p.src); p.dst = tp.mirror.translate(p.dst); }
+        for (auto& p : h.unpack) p.dst = tp.mirror.translate(p.dst);
+    }
     if (h.total_send > 0 && cudaMalloc(reinterpret_cast<void**>(&tp.send_buf), h.total_send) != cudaSuccess) {
         set_last_error("transform: cudaMalloc of the send buffer failed");
         return COSMA_B200_OUT_OF_MEMORY;
@@ -68,6 +90,10 @@ int transform_plan_run(TransformPlan& tp, cudaStream_t stream) {
     if (st != COSMA_B200_OK) return st;
     const auto& h = tp.host;
     tp.last_launches = 0;
+    if (tp.mirror.active()) {
+        st = tp.mirror.upload(stream);
+        if (st != COSMA_B200_OK) return st;
+    }
     st = relayout_launch(tp.stage1, tp.dtype, stream, &tp.last_launches);
     if (st != COSMA_B200_OK) return st;
     if (h.total_send > 0 || h.total_recv > 0) {
@@ -85,11 +111,13 @@ int transform_plan_run(TransformPlan& tp, cudaStream_t stream) {
         }
         COSMA_B200_NCCL_TRY(N->GroupEnd());
     }
-    return relayout_launch(tp.stage2, tp.dtype, stream, &tp.last_launches);
+    st = relayout_launch(tp.stage2, tp.dtype, stream, &tp.last_launches);
+    if (st != COSMA_B200_OK) return st;
+    return tp.mirror.active() ? tp.mirror.download(stream) : COSMA_B200_OK;
 }
 
-// grid_layout from the C struct (reference grid_from_clayout, src/cosma/cinterface.cpp:10-52)
-costa::grid_layout layout_from_c(const cosma_b200_layout& l, char ordering, int nranks) {
+// erased_layout from the C struct (reference grid_from_clayout, src/cosma/cinterface.cpp:10-52)
+costa::erased_layout layout_from_c(const cosma_b200_layout& l, char ordering, int nranks) {
     std::vector<int> br(l.nlocalblocks), bc(l.nlocalblocks);
     std::vector<void*> data(l.nlocalblocks);
     std::vector<std::int64_t> ld(l.nlocalblocks);
@@ -99,7 +127,7 @@ costa::grid_layout layout_from_c(const cosma_b200_layout& l, char ordering, int 
         data[b] = l.localblocks[b].data;
         ld[b] = l.localblocks[b].ld;
     }
-    costa::grid_layout g = costa::custom_layout(l.rowblocks, l.colblocks, l.rowsplit, l.colsplit, l.owners, l.nlocalblocks, br.data(),
+    costa::erased_layout g = costa::erased_custom_layout(l.rowblocks, l.colblocks, l.rowsplit, l.colsplit, l.owners, l.nlocalblocks, br.data(),
                                                 bc.data(), data.data(), ld.data(), ordering);
     g.grid.n_ranks = nranks;
     return g;
@@ -120,7 +148,7 @@ int cosma_b200_transform_plan_create(void* comm, int rank, int nranks, char dtyp
     Comm* c = static_cast<Comm*>(comm);
     if (c) { rank = c->rank; nranks = c->size; }
     try {
-        std::vector<costa::grid_layout> F, T;
+        std::vector<costa::erased_layout> F, T;
         F.reserve(n);
         T.reserve(n);
         for (int i = 0; i < n; ++i) {
@@ -236,7 +264,7 @@ int cosma_b200_scalapack_layout(int lld, int mat_rows, int mat_cols, int ia, int
                                 int64_t* local_offset) {
     try {
         // element offsets: plan with a null base pointer and 1-byte elements
-        const costa::grid_layout l = costa::get_scalapack_layout(lld, mat_rows, mat_cols, ia, ja, sub_m, sub_n, mb, nb, nprow, npcol,
+        const costa::erased_layout l = costa::erased_scalapack_layout(lld, mat_rows, mat_cols, ia, ja, sub_m, sub_n, mb, nb, nprow, npcol,
                                                                  grid_order, rsrc, csrc, nullptr, 1, data_ordering, rank);
         if (rowblocks) *rowblocks = l.grid.grid.n_rows();
         if (colblocks) *colblocks = l.grid.grid.n_cols();

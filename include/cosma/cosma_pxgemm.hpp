@@ -1,0 +1,20 @@
+// cosma::pxgemm<T> -- p?gemm on 2D block-cyclic matrices, reference signature (src/cosma/cosma_pxgemm.hpp:15-33,
+// cosma_pxgemm.cpp:16-388): sub(C) = alpha * op(sub(A)) * op(sub(B)) + beta * sub(C). The process grid and communicator
+// come from BLACS for the context in desc[1]. a, b, c: the rank's local arrays in host or device memory.
+#pragma once
+#include <cosma/scalapack.hpp>
+
+#include <complex>
+
+namespace cosma {
+using zdouble_t = std::complex<double>;
+using zfloat_t = std::complex<float>;
+
+template <typename T>
+void pxgemm(const char trans_a, const char trans_b, const int m, const int n, const int k, const T alpha, const T* a, const int ia, const int ja,
+            const int* desca, const T* b, const int ib, const int jb, const int* descb, const T beta, T* c, const int ic, const int jc,
+            const int* descc);
+
+// releases the grid handles cached per BLACS context (call before Cblacs_gridexit / MPI_Finalize)
+void pxgemm_release_grids();
+}  // namespace cosma

@@ -97,6 +97,11 @@ COSMA_B200_API int cosma_b200_comm_destroy(void* comm);
  * "pm2,pn2,pk2". dtype: 's' | 'd' | 'c' | 'z' (float, double, complex float, complex double). */
 COSMA_B200_API int cosma_b200_plan_create(void* comm, int rank, int nranks, int m, int n, int k, const char* steps, char dtype,
                                           void** plan_out);
+/* Same for an explicit cosma::Strategy (reference multiply(A, B, C, strategy, comm, alpha, beta), multiply.hpp:47-54): the
+ * strategy's own rank count P (<= ranks of comm; ranks >= P idle, multiply.cpp:258-260) and its step list, which may be
+ * empty when P == 1. `steps` is never completed or replaced by the automatic strategy here. */
+COSMA_B200_API int cosma_b200_plan_create_for_strategy(void* comm, int rank, int nranks, int m, int n, int k, int P, const char* steps,
+                                                       char dtype, void** plan_out);
 COSMA_B200_API int cosma_b200_plan_destroy(void* plan);
 /* Arena sizes in elements. matrix: 0 = A, 1 = B, 2 = C. The first initial_elements of an arena are the rank's local
  * matrix in the reference's layout (CosmaMatrix::matrix_pointer(), matrix_size(); src/cosma/matrix.hpp:26-213); the
@@ -295,6 +300,19 @@ COSMA_B200_API int cosma_b200_zgemm_host(void* stream, int64_t m, int64_t n, int
 COSMA_B200_API int cosma_b200_last_launch_count(void);
 /* Frees the device staging workspace cached by the *_host entry points (thread-local). */
 COSMA_B200_API void cosma_b200_release_workspace(void);
+
+/* ---- host memory and device housekeeping for C++ / Fortran hosts that do not link the CUDA runtime ----------------
+ * The reference pins the buffers of its memory pool so that Tiled-MM's copies are asynchronous (src/cosma/
+ * pinned_buffers.cpp:10-40, memory_pool.cpp:153-170, local_multiply.cpp:341-347). host_alloc returns page-locked memory
+ * (cudaHostAlloc, portable); host_register / host_unregister pin and unpin caller memory in place. */
+COSMA_B200_API int cosma_b200_host_alloc(void** ptr, uint64_t bytes);
+COSMA_B200_API int cosma_b200_host_free(void* ptr);
+COSMA_B200_API int cosma_b200_host_register(void* ptr, uint64_t bytes);
+COSMA_B200_API int cosma_b200_host_unregister(void* ptr);
+COSMA_B200_API int cosma_b200_device_count(int* count);
+COSMA_B200_API int cosma_b200_set_device(int device);
+/* Blocks until everything queued on `stream` (NULL: the default stream) has finished. */
+COSMA_B200_API int cosma_b200_stream_synchronize(void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,70 +1,64 @@
-// costa:: layouts -- how a distributed matrix is cut into blocks, who owns each block and where the blocks of the
-// calling rank sit in (device) memory. Restates the data model of the reference's COSTA
-// (libs/COSTA/src/costa/grid2grid/grid2D.hpp, grid_layout.hpp:9-181, block.hpp:64-137, layout.hpp:34-86,
-// scalapack_layout.cpp:152-285) in type-erased form: the element type only matters to the kernels, so a layout
-// carries byte pointers and leading dimensions in ELEMENTS, and the transform is told the element size.
+// Public layout constructors of COSTA with the reference's signatures (libs/COSTA/src/costa/layout.hpp:14-100):
+// custom_layout<T>, custom_grid, block_cyclic_layout<T>, block_cyclic_grid. Header-only over the planner in
+// <costa/erased_layout.hpp>. Pointers may be host or device memory.
 #pragma once
-#include <cstdint>
-#include <vector>
+#include <costa/grid2grid/grid_layout.hpp>
+
+#include <stdexcept>
 
 namespace costa {
 
-// grid lines: block (i, j) covers rows [rows_split[i], rows_split[i+1]) x cols [cols_split[j], cols_split[j+1])
-struct grid2D {
-    std::vector<int> rows_split{0};
-    std::vector<int> cols_split{0};
-    int n_rows() const { return static_cast<int>(rows_split.size()) - 1; }
-    int n_cols() const { return static_cast<int>(cols_split.size()) - 1; }
-    int total_rows() const { return rows_split.back(); }
-    int total_cols() const { return cols_split.back(); }
+// a local block as the C / Fortran interfaces describe it
+struct block_t {
+    void* data;
+    int ld;
+    int row;
+    int col;
 };
 
-struct assigned_grid2D {
-    grid2D grid;
-    std::vector<int> owners;  // row-major: owners[i * n_cols + j] (reference cinterface.cpp:40-45)
+inline assigned_grid2D custom_grid(const int rowblocks, const int colblocks, const int* rowsplit, const int* colsplit, const int* owners) {
+    erased_layout e = erased_custom_layout(rowblocks, colblocks, rowsplit, colsplit, owners, 0, nullptr, nullptr, nullptr, nullptr, 'C');
     int n_ranks = 1;
-    int owner(int i, int j) const { return owners[static_cast<size_t>(i) * grid.n_cols() + j]; }
-    // the grid of the transposed matrix (reference assigned_grid2D::transpose, grid2D.cpp)
-    assigned_grid2D transposed() const;
-    // relabel ranks: owner r becomes perm[r] (grid_layout::reorder_ranks)
-    void reorder_ranks(const std::vector<int>& perm);
-};
+    for (int o : e.grid.owners) n_ranks = o + 1 > n_ranks ? o + 1 : n_ranks;
+    e.grid.n_ranks = n_ranks;
+    return e.grid;
+}
 
-// a block of the calling rank: grid coordinates + where its (bi, bj) storage starts
-struct local_block {
-    int bi = 0, bj = 0;
-    void* data = nullptr;      // device (or host, for planning-only tests) address of element (0, 0) of the block
-    std::int64_t ld = 0;       // leading dimension in elements (column stride if ordering 'C', row stride if 'R')
-};
+template <typename T>
+grid_layout<T> custom_layout(const int rowblocks, const int colblocks, const int* rowsplit, const int* colsplit, const int* owners,
+                             const int nlocalblocks, const block_t* localblocks, const char ordering) {
+    assigned_grid2D g = custom_grid(rowblocks, colblocks, rowsplit, colsplit, owners);
+    std::vector<block<T>> loc;
+    loc.reserve(nlocalblocks);
+    for (int b = 0; b < nlocalblocks; ++b) {
+        const block_t& cb = localblocks[b];
+        if (cb.row < 0 || cb.row >= rowblocks || cb.col < 0 || cb.col >= colblocks) throw std::runtime_error("custom_layout: block coordinates outside the grid");
+        loc.emplace_back(g, cb.row, cb.col, static_cast<T*>(cb.data), cb.ld);
+    }
+    return grid_layout<T>(std::move(g), local_blocks<T>(std::move(loc)), ordering);
+}
 
-struct grid_layout {
-    assigned_grid2D grid;
-    std::vector<local_block> blocks;  // blocks owned by the calling rank
-    char ordering = 'C';              // storage order of every local block
-    int num_rows() const { return grid.grid.total_rows(); }
-    int num_cols() const { return grid.grid.total_cols(); }
-};
+inline assigned_grid2D block_cyclic_grid(const int m, const int n, const int block_m, const int block_n, const int i, const int j,
+                                         const int sub_m, const int sub_n, const int proc_m, const int proc_n, const char rank_grid_ordering,
+                                         const int rsrc, const int csrc) {
+    erased_layout e = erased_scalapack_layout(/*lld=*/1, m, n, i, j, sub_m, sub_n, block_m, block_n, proc_m, proc_n, rank_grid_ordering, rsrc, csrc,
+                                              nullptr, 1, 'C', /*rank=*/-1);
+    e.grid.n_ranks = proc_m * proc_n;
+    return e.grid;
+}
 
-// custom_layout (reference layout.hpp:34-48): arrays in the shape of the C interface's struct layout
-grid_layout custom_layout(int rowblocks, int colblocks, const int* rowsplit, const int* colsplit, const int* owners,
-                          int nlocalblocks, const int* block_rows, const int* block_cols, void* const* block_data,
-                          const std::int64_t* block_ld, char ordering);
-
-// split points of [begin, end) cut at multiples of blk_len, shifted to start at 0 (scalapack_layout.cpp:152-177)
-std::vector<int> line_split(int begin, int end, int blk_len);
-
-// rank <-> coordinates in a process grid ordered 'R' (row-major) or 'C' (column-major) (scalapack_layout.cpp:11-57)
-int rank_from_grid(int prow, int pcol, int nprow, int npcol, char order);
-void rank_to_grid(int rank, int nprow, int npcol, char order, int* prow, int* pcol);
-
-// Block-cyclic (ScaLAPACK) layout of the sub-matrix sub(A) = A(ia : ia+sub_m-1, ja : ja+sub_n-1), 1-based ia/ja
-// (reference get_scalapack_layout, scalapack_layout.cpp:178-285). ptr = local array of the WHOLE matrix A on `rank`
-// with leading dimension lld; elem_bytes turns element offsets into addresses.
-grid_layout get_scalapack_layout(int lld, int mat_rows, int mat_cols, int ia, int ja, int sub_m, int sub_n, int mb, int nb,
-                                 int nprow, int npcol, char grid_order, int rsrc, int csrc, void* ptr, int elem_bytes,
-                                 char data_ordering, int rank);
-
-// ScaLAPACK NUMROC: rows/cols of a block-cyclic dimension that land on process coordinate iproc
-int numroc(int n, int nb, int iproc, int isrcproc, int nprocs);
+template <typename T>
+grid_layout<T> block_cyclic_layout(const int m, const int n, const int block_m, const int block_n, const int i, const int j, const int sub_m,
+                                   const int sub_n, const int p_m, const int p_n, const char order, const int rsrc, const int csrc, T* ptr,
+                                   const int lld, const char ordering, const int rank) {
+    erased_layout e = erased_scalapack_layout(lld, m, n, i, j, sub_m, sub_n, block_m, block_n, p_m, p_n, order, rsrc, csrc, ptr, static_cast<int>(sizeof(T)),
+                                              ordering, rank);
+    e.grid.n_ranks = p_m * p_n;
+    std::vector<block<T>> loc;
+    loc.reserve(e.blocks.size());
+    for (const auto& b : e.blocks) loc.emplace_back(e.grid, b.bi, b.bj, static_cast<T*>(b.data), static_cast<int>(b.ld));
+    assigned_grid2D g = e.grid;
+    return grid_layout<T>(std::move(g), local_blocks<T>(std::move(loc)), ordering);
+}
 
 }  // namespace costa

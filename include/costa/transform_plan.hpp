@@ -11,7 +11,7 @@
 // 67-164), pack plainly and apply op/alpha/beta when unpacking (communication_data.cpp:166-244). Sender and receiver
 // enumerate the overlay cells in the same canonical order, so the packed images agree without exchanging metadata.
 #pragma once
-#include <costa/layout.hpp>
+#include <costa/erased_layout.hpp>
 
 #include <cstdint>
 #include <vector>
@@ -34,8 +34,8 @@ struct piece {
 };
 
 struct transform_spec {
-    const grid_layout* from = nullptr;
-    const grid_layout* to = nullptr;
+    const erased_layout* from = nullptr;
+    const erased_layout* to = nullptr;
     char op = 'N';                // 'N' | 'T' | 'C', applied to the source
     double alpha[2] = {1.0, 0.0};
     double beta[2] = {0.0, 0.0};

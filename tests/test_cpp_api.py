@@ -1,0 +1,169 @@
+"""The C++ host layer (libcosma.so and friends: cosma::multiply / CosmaMatrix / multiply_using_layout, costa::transform, the C
+interface, the ScaLAPACK p?gemm symbols) driven by C++ test programs that read like the reference's own tests
+(tests/cpp/*.cpp <-> reference tests/multiply.cpp, scalar_matmul.cpp, multiply_using_layout.cpp, pdgemm.cpp).
+
+CPU part: the libraries build with plain g++, export the reference's symbols, the MPI-name subset works across processes,
+the coordinate maps match the reference's goldens, and compute entry points fail loudly without a GPU.
+GPU part (-m gpu): the programs run on 1 rank and, when the box has the GPUs, on 2 / 4 / 8 ranks (one per GPU)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CPP = os.path.join(HERE, "cpp")
+BIN = os.path.join(CPP, "bin")
+LIBDIR = os.path.join(ROOT, "cosma_b200", "lib")
+sys.path.insert(0, ROOT)
+
+PROGRAMS = {
+    # name: (source, extra libraries, needs the oracle)
+    "test_api_cpu": (os.path.join(CPP, "test_api_cpu.cpp"), [], False),
+    "test_process_group": (os.path.join(CPP, "test_process_group.cpp"), [], False),
+    "test_multiply": (os.path.join(CPP, "test_multiply.cpp"), [], True),
+    "test_multiply_using_layout": (os.path.join(CPP, "test_multiply_using_layout.cpp"), [], True),
+    "test_pxgemm": (os.path.join(CPP, "test_pxgemm.cpp"), ["cosma_prefixed_pxgemm", "cosma_pxgemm", "cosma_pxgemm_cpp", "cosma_blacs_lite"], True),
+    "cosma_miniapp": (os.path.join(ROOT, "miniapp", "cosma_miniapp.cpp"), [], False),
+    "pxgemm_miniapp": (os.path.join(ROOT, "miniapp", "pxgemm_miniapp.cpp"), ["cosma_pxgemm_cpp", "cosma_blacs_lite"], False),
+}
+
+
+@pytest.fixture(scope="session")
+def host_libs(lib):
+    from cosma_b200 import build
+    return build.build_host()
+
+
+def program(name, oracle=None):
+    src, libs, needs_oracle = PROGRAMS[name]
+    out = os.path.join(BIN, name)
+    os.makedirs(BIN, exist_ok=True)
+    deps = [src] + [os.path.join(CPP, f) for f in os.listdir(CPP) if f.endswith(".hpp")] + [os.path.join(LIBDIR, "libcosma.so")]
+    if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(d) for d in deps):
+        return out
+    cmd = ["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", out, "-L", LIBDIR]
+    cmd += ["-l" + l for l in libs] + ["-lcosma", "-lcosma_b200", "-Wl,-rpath," + LIBDIR]
+    if needs_oracle:
+        odir = os.path.join(ROOT, "oracle")
+        cmd += ["-L", odir, "-loracle", "-Wl,-rpath," + odir]
+    subprocess.check_call(cmd)
+    return out
+
+
+def run_ranks(np_, argv, timeout=600):
+    from cosma_b200.launch import launch
+    code, outs = launch(np_, argv, timeout=timeout, capture=True)
+    text = "\n".join("--- rank %d ---\n%s" % (r, o) for r, o in enumerate(outs))
+    assert code == 0, text[-6000:]
+    return outs[0]
+
+
+# ---- CPU --------------------------------------------------------------------------------------------------------------
+
+def test_host_libraries_export_the_reference_symbols(host_libs):
+    def symbols(name):
+        out = subprocess.check_output(["nm", "-D", "--defined-only", "-C", os.path.join(LIBDIR, name)], text=True)
+        while "> >" in out:
+            out = out.replace("> >", ">>")
+        return out
+    core = symbols("libcosma.so")
+    for t in ("float", "double", "std::complex<float>", "std::complex<double>"):
+        assert "void cosma::multiply<%s>(cosma::CosmaMatrix<%s>&" % (t, t) in core, t
+        assert "void cosma::multiply_using_layout<%s>(costa::grid_layout<%s>&" % (t, t) in core, t
+        assert "cosma::CosmaMatrix<%s>::matrix_size() const" % t in core, t
+        assert "cosma::get_context_instance<%s>()" % t in core, t
+        assert "void costa::transform<%s>(costa::grid_layout<%s>&, costa::grid_layout<%s>&, char, %s, %s" % (t, t, t, t, t) in core, t
+    for f in ("smultiply_using_layout", "dmultiply_using_layout", "cmultiply_using_layout", "zmultiply_using_layout"):
+        assert " T %s\n" % f in core, f
+    assert "cosma::Strategy::Strategy(int, int, int, unsigned long, long long, bool, bool, bool)" in core
+    px = symbols("libcosma_pxgemm.so")
+    pre = symbols("libcosma_prefixed_pxgemm.so")
+    for t in "sdcz":
+        for name in ("p%sgemm" % t, "p%sgemm_" % t, ("p%sgemm" % t).upper(), ("p%sgemm_" % t).upper()):
+            assert " T %s\n" % name in px, name
+        for name in ("cosma_p%sgemm" % t, "cosma_p%sgemm_" % t, "COSMA_P%sGEMM" % t.upper(), "COSMA_P%sGEMM_" % t.upper()):
+            assert " T %s\n" % name in pre, name
+    cpp = symbols("libcosma_pxgemm_cpp.so")
+    assert "void cosma::pxgemm<double>(char, char, int, int, int, double, double const*" in cpp
+    assert "void cosma::pxgemm<std::complex<double>>(" in cpp
+
+
+@pytest.mark.parametrize("header", ["cosma/multiply.hpp", "cosma/matrix.hpp", "cosma/context.hpp", "cosma/strategy.hpp", "cosma/mapper.hpp",
+                                    "cosma/cinterface.hpp", "cosma/cosma_pxgemm.hpp", "cosma/pxgemm.h", "cosma/prefixed_pxgemm.h",
+                                    "costa/layout.hpp", "costa/grid2grid/transform.hpp", "costa/grid2grid/transformer.hpp",
+                                    "costa/grid2grid/scalapack_layout.hpp", "cosma_b200.h"])
+def test_public_headers_are_self_contained(header, tmp_path):
+    src = tmp_path / "t.cpp"
+    src.write_text("#include <%s>\nint main() { return 0; }\n" % header)
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_c_abi_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text("#include <cosma_b200.h>\nint main(void) { return cosma_b200_version() == 0; }\n")
+    subprocess.check_call(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_api_on_cpu(host_libs):
+    out = subprocess.run([program("test_api_cpu")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "failed = 0" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("np_", [1, 2, 5])
+def test_process_group(host_libs, np_):
+    out = run_ranks(np_, [program("test_process_group")], timeout=120)
+    assert "failed = 0" in out, out
+
+
+def test_compute_fails_loudly_without_gpu(host_libs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    exe = program("cosma_miniapp")
+    out = subprocess.run([exe, "-m", "64", "-n", "64", "-k", "64"], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0
+    assert "no CPU fallback" in (out.stdout + out.stderr) or "cuda" in (out.stdout + out.stderr).lower()
+
+
+# ---- GPU --------------------------------------------------------------------------------------------------------------
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _rank_counts():
+    return [n for n in (1, 2, 4, 8) if n == 1 or n <= _gpus()]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["test_multiply", "test_multiply_using_layout", "test_pxgemm"])
+@pytest.mark.parametrize("np_", [1, 2, 4, 8])
+def test_cpp_program(host_libs, oracle, name, np_):
+    if np_ > 1 and np_ > _gpus():
+        pytest.skip("needs %d GPUs" % np_)
+    out = run_ranks(np_, [program(name)], timeout=900)
+    assert "failed = 0" in out, out[-4000:]
+    assert "checks passed (all ranks) = 0," not in out, out[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("np_", [1, 2, 4, 8])
+@pytest.mark.parametrize("dtype", ["double", "zdouble", "float", "zfloat"])
+def test_cosma_miniapp(host_libs, dtype, np_):
+    if np_ > 1 and np_ > _gpus():
+        pytest.skip("needs %d GPUs" % np_)
+    out = run_ranks(np_, [program("cosma_miniapp"), "-m", "1024", "-n", "768", "-k", "1280", "-r", "2", "-t", dtype], timeout=600)
+    assert "COSMA TIMES [ms] =" in out, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("np_", [1, 2, 4, 8])
+def test_pxgemm_miniapp(host_libs, np_):
+    if np_ > 1 and np_ > _gpus():
+        pytest.skip("needs %d GPUs" % np_)
+    out = run_ranks(np_, [program("pxgemm_miniapp"), "-m", "1024", "-n", "768", "-k", "512", "--block_a", "128,128", "--block_b", "64,64",
+                          "--block_c", "128,32", "--trans_a", "T", "-r", "2", "--type", "zdouble"], timeout=600)
+    assert "COSMA TIMES [ms] =" in out, out
