@@ -3,6 +3,7 @@
 #include "../../../include/cosma_b200.h"
 #include <cosma/mapper.hpp>
 #include <cosma/strategy.hpp>
+#include <costa/grid2grid/comm_volume.hpp>
 
 #include <cstring>
 #include <string>
@@ -79,6 +80,54 @@ int cosma_b200_mapper_global_coordinates(char label, int m, int n, int k, int P,
         const auto res = mapper.global_coordinates(local_idx, rank);
         *gi = res.first;
         *gj = res.second;
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        cosma_b200::set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+// costa::communication_volume between two grids given as in struct cosma_b200_layout (no local blocks needed) and
+// costa::optimal_reordering on a dense volume matrix indexed [min(u,v) * n_ranks + max(u,v)] (see comm_volume.hpp).
+int cosma_b200_comm_volume(int rowblocks_a, int colblocks_a, const int* rowsplit_a, const int* colsplit_a, const int* owners_a, int rowblocks_b,
+                           int colblocks_b, const int* rowsplit_b, const int* colsplit_b, const int* owners_b, char trans, int n_ranks,
+                           long long* volume) {
+    try {
+        if (!volume || n_ranks < 1) return COSMA_B200_INVALID_ARG;
+        auto grid = [n_ranks](int rb, int cb, const int* rs, const int* cs, const int* own) {
+            costa::assigned_grid2D g;
+            g.grid.rows_split.assign(rs, rs + rb + 1);
+            g.grid.cols_split.assign(cs, cs + cb + 1);
+            g.owners.assign(own, own + static_cast<size_t>(rb) * cb);
+            g.n_ranks = n_ranks;
+            return g;
+        };
+        const costa::comm_volume vol = costa::communication_volume(grid(rowblocks_a, colblocks_a, rowsplit_a, colsplit_a, owners_a),
+                                                                   grid(rowblocks_b, colblocks_b, rowsplit_b, colsplit_b, owners_b), trans);
+        for (long long i = 0; i < static_cast<long long>(n_ranks) * n_ranks; ++i) volume[i] = 0;
+        for (const auto& kv : vol.volume) {
+            if (kv.first.src < 0 || kv.first.dest >= n_ranks) return COSMA_B200_INVALID_ARG;
+            volume[static_cast<long long>(kv.first.src) * n_ranks + kv.first.dest] = static_cast<long long>(kv.second);
+        }
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        cosma_b200::set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+int cosma_b200_optimal_reordering(int n_ranks, const long long* volume, int* permutation, int* reordered) {
+    try {
+        if (!volume || !permutation || n_ranks < 1) return COSMA_B200_INVALID_ARG;
+        costa::comm_volume vol;
+        for (int u = 0; u < n_ranks; ++u)
+            for (int v = u; v < n_ranks; ++v)
+                if (volume[static_cast<long long>(u) * n_ranks + v] > 0)
+                    vol.volume[costa::edge_t(u, v)] = static_cast<size_t>(volume[static_cast<long long>(u) * n_ranks + v]);
+        bool re = false;
+        const std::vector<int> perm = costa::optimal_reordering(vol, n_ranks, re);
+        for (int i = 0; i < n_ranks; ++i) permutation[i] = perm[i];
+        if (reordered) *reordered = re ? 1 : 0;
         return COSMA_B200_OK;
     } catch (const std::exception& e) {
         cosma_b200::set_last_error(e.what());

@@ -187,6 +187,14 @@ COSMA_B200_API int cosma_b200_scalapack_layout(int lld, int mat_rows, int mat_co
                                                char data_ordering, int rank, int* rowblocks, int* colblocks, int* rowsplit,
                                                int* colsplit, int* owners, int* nlocal, int* local_row, int* local_col,
                                                int64_t* local_offset);
+/* costa::communication_volume (libs/COSTA/src/costa/grid2grid/transform.cpp:9-44): elements exchanged between every pair of
+ * ranks when a matrix moves from grid a (transposed first when trans != 'N') to grid b; volume is n_ranks x n_ranks,
+ * entry [u * n_ranks + v], u <= v, counts both directions, [u * n_ranks + u] is what stays on rank u.
+ * costa::optimal_reordering (ranks_reordering.cpp:4-61): the greedy matching on that graph; permutation[r] = new label. */
+COSMA_B200_API int cosma_b200_comm_volume(int rowblocks_a, int colblocks_a, const int* rowsplit_a, const int* colsplit_a, const int* owners_a,
+                                          int rowblocks_b, int colblocks_b, const int* rowsplit_b, const int* colsplit_b, const int* owners_b,
+                                          char trans, int n_ranks, long long* volume);
+COSMA_B200_API int cosma_b200_optimal_reordering(int n_ranks, const long long* volume, int* permutation, int* reordered);
 /* ScaLAPACK NUMROC. */
 COSMA_B200_API int cosma_b200_numroc(int n, int nb, int iproc, int isrcproc, int nprocs);
 

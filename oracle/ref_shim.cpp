@@ -266,3 +266,41 @@ extern "C" int ref_transform_p1(char dtype, const ref_layout* from, char from_or
         return -1;
     }
 }
+
+// ---- communication volume and rank relabelling of the unmodified reference ------------------------------------------
+// costa::communication_volume (transform.cpp:9-44) between two custom grids and costa::optimal_reordering
+// (ranks_reordering.cpp:4-61). Volumes are returned as a dense n_ranks x n_ranks matrix indexed [min(u,v)][max(u,v)].
+#include <costa/grid2grid/ranks_reordering.hpp>
+
+extern "C" int ref_comm_volume(int rb_a, int cb_a, const int* rs_a, const int* cs_a, const int* own_a, int rb_b, int cb_b, const int* rs_b,
+                               const int* cs_b, const int* own_b, char trans, int n_ranks, long long* out) {
+    try {
+        auto ga = costa::custom_grid(rb_a, cb_a, rs_a, cs_a, own_a);
+        auto gb = costa::custom_grid(rb_b, cb_b, rs_b, cs_b, own_b);
+        auto vol = costa::communication_volume(ga, gb, trans);
+        for (long long i = 0; i < (long long)n_ranks * n_ranks; ++i) out[i] = 0;
+        for (const auto& kv : vol.volume) {
+            const int u = std::min(kv.first.src, kv.first.dest), v = std::max(kv.first.src, kv.first.dest);
+            out[(long long)u * n_ranks + v] += (long long)kv.second;
+        }
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
+
+extern "C" int ref_optimal_reordering(int n_ranks, const long long* volume, int* permutation, int* reordered) {
+    try {
+        costa::comm_volume vol;
+        for (int u = 0; u < n_ranks; ++u)
+            for (int v = u; v < n_ranks; ++v)
+                if (volume[(long long)u * n_ranks + v] > 0) vol.volume[costa::edge_t{u, v}] = (size_t)volume[(long long)u * n_ranks + v];
+        bool re = false;
+        auto perm = costa::optimal_reordering(vol, n_ranks, re);
+        for (int i = 0; i < n_ranks; ++i) permutation[i] = perm[i];
+        *reordered = re ? 1 : 0;
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
