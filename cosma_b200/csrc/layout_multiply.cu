@@ -11,9 +11,12 @@
 // its context, context.cpp:80-125, and re-derives the COSTA messages on every call).
 #include "exec_internal.h"
 
+#include <cosma/environment_variables.hpp>
 #include <costa/erased_layout.hpp>
+#include <costa/grid2grid/comm_volume.hpp>
 
 #include <cstring>
+#include <mutex>
 
 namespace cosma_b200 {
 
@@ -34,6 +37,10 @@ struct LayoutMultiplyState {
     int last_launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start | A,B relayouted | multiplied | C relayouted
     std::int64_t last_elements[4] = {0, 0, 0, 0};              // in: local, remote; out: local, remote
+    // rank relabelling (reference multiply.cpp:136-152): this rank plays COSMA rank perm[rank] on `relabelled`, the parent
+    // communicator re-split with key perm[rank]; identity -> relabelled == nullptr and the plan runs on the parent
+    std::vector<int> perm;
+    Comm* relabelled = nullptr;
     ~LayoutMultiplyState() {
         transforms.clear();
         for (auto& e : ev)
@@ -41,6 +48,10 @@ struct LayoutMultiplyState {
         for (auto& a : arena)
             if (a) cudaFree(a);
         if (plan) cosma_b200_plan_destroy(plan);
+        if (relabelled) {
+            if (relabelled->comm && nccl()) nccl()->CommDestroy(relabelled->comm);
+            delete relabelled;
+        }
     }
 };
 
@@ -137,8 +148,48 @@ int scale_layout(char dtype, const costa::erased_layout& C, const double* beta, 
     return st;
 }
 
-int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, LayoutMultiplyState** out) {
-    const std::string key = std::string(1, dtype) + ":" + std::to_string(m) + ":" + std::to_string(n) + ":" + std::to_string(k) + ":" + (steps ? steps : "");
+// COSMA's native layouts of A, B, C as assigned grids with owners in COSMA rank labels (Mapper::get_layout_grid, reference
+// mapper.cpp:369-414): global information, the same on every rank, cached per problem
+struct NativeGrids {
+    costa::assigned_grid2D g[3];
+};
+const NativeGrids& native_grids(int nranks, int m, int n, int k, const char* steps) {
+    static std::mutex mu;
+    static std::map<std::string, NativeGrids> cache;
+    const std::string key = std::to_string(nranks) + ":" + std::to_string(m) + ":" + std::to_string(n) + ":" + std::to_string(k) + ":" + (steps ? steps : "");
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    NativeGrids ng;
+    const cosma::Strategy strategy = cosma::parse_strategy(m, n, k, static_cast<size_t>(nranks), steps ? steps : "");
+    for (int x = 0; x < 3; ++x) {
+        const cosma::Mapper mapper("ABC"[x], strategy, 0);
+        ng.g[x].grid.rows_split = mapper.row_split();
+        ng.g[x].grid.cols_split = mapper.col_split();
+        ng.g[x].n_ranks = nranks;
+        const auto owners = mapper.grid_owners();
+        const int nr = ng.g[x].grid.n_rows(), nc = ng.g[x].grid.n_cols();
+        ng.g[x].owners.resize(static_cast<size_t>(nr) * nc);
+        for (int i = 0; i < nr; ++i)
+            for (int j = 0; j < nc; ++j) ng.g[x].owners[static_cast<size_t>(i) * nc + j] = owners[i][j];
+    }
+    return cache.emplace(key, std::move(ng)).first->second;
+}
+
+bool relabelling_enabled() {
+    static const bool on = cosma::get_bool_env_var("COSMA_B200_REORDER_RANKS", true);
+    return on;
+}
+
+// perm: this rank plays COSMA rank perm[rank] (an involution; empty or identity = no relabelling)
+int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, const std::vector<int>& perm, LayoutMultiplyState** out) {
+    std::string key = std::string(1, dtype) + ":" + std::to_string(m) + ":" + std::to_string(n) + ":" + std::to_string(k) + ":" + (steps ? steps : "");
+    bool relabel = false;
+    for (size_t r = 0; r < perm.size(); ++r) relabel = relabel || perm[r] != static_cast<int>(r);
+    if (relabel) {
+        key += ":perm";
+        for (int v : perm) key += "," + std::to_string(v);
+    }
     auto it = c->layout_states.find(key);
     if (it != c->layout_states.end()) {
         *out = it->second;
@@ -146,7 +197,18 @@ int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, Layou
     }
     auto st = std::make_unique<LayoutMultiplyState>();
     st->dtype = dtype;
-    int rc = cosma_b200_plan_create(c, c->rank, c->size, m, n, k, steps ? steps : "", dtype, &st->plan);
+    Comm* pc = c;  // the communicator the multiply runs on
+    if (relabel) {
+        st->perm = perm;
+        ncclComm_t sub = nullptr;
+        COSMA_B200_NCCL_TRY(nccl()->CommSplit(c->comm, 0, perm[c->rank], &sub, nullptr));
+        st->relabelled = new Comm;
+        st->relabelled->comm = sub;
+        st->relabelled->rank = perm[c->rank];
+        st->relabelled->size = c->size;
+        pc = st->relabelled;
+    }
+    int rc = cosma_b200_plan_create(pc, pc->rank, pc->size, m, n, k, steps ? steps : "", dtype, &st->plan);
     if (rc != COSMA_B200_OK) return rc;
     Plan* plan = static_cast<Plan*>(st->plan);
     const int eb = dtype_bytes(dtype);
@@ -168,11 +230,12 @@ int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, Layou
         const auto owners = mapper.grid_owners();
         const int nr = L.grid.grid.n_rows(), nc = L.grid.grid.n_cols();
         L.grid.owners.resize(static_cast<size_t>(nr) * nc);
+        // owners in the PARENT communicator's labels: COSMA rank q is played by parent rank perm[q] (perm is an involution)
         for (int i = 0; i < nr; ++i)
-            for (int j = 0; j < nc; ++j) L.grid.owners[static_cast<size_t>(i) * nc + j] = owners[i][j];
-        if (c->rank < P) {
-            const auto& blocks = mapper.initial_layout(c->rank);
-            const auto& offs = mapper.blocks_offsets(c->rank);
+            for (int j = 0; j < nc; ++j) L.grid.owners[static_cast<size_t>(i) * nc + j] = relabel ? perm[owners[i][j]] : owners[i][j];
+        if (pc->rank < P) {
+            const auto& blocks = mapper.initial_layout(pc->rank);
+            const auto& offs = mapper.blocks_offsets(pc->rank);
             for (size_t b = 0; b < blocks.size(); ++b) {
                 const auto& rs = L.grid.grid.rows_split;
                 const auto& cs = L.grid.grid.cols_split;
@@ -196,8 +259,21 @@ int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, 
     // corner cases allowed by the BLAS standard (multiply.cpp:96-109, cosma_pxgemm.cpp:36-46)
     if (m == 0 || n == 0) return COSMA_B200_OK;
     if (k == 0 || is_zero(alpha, cplx)) return scale_layout(dtype, C, beta, stream);
+    // rank relabelling (reference multiply.cpp:136-152, cosma_pxgemm.cpp:255-271): relabel the COSMA ranks so
+    // that as much of A, B and C as possible is already where COSMA's layout wants it; every rank derives the same
+    // permutation from the global grids
+    std::vector<int> perm;
+    if (c->size > 1 && c->comm && relabelling_enabled()) {
+        const NativeGrids& ng = native_grids(c->size, m, n, k, steps);
+        costa::comm_volume vol = costa::communication_volume(A.grid, ng.g[0], ta);
+        vol += costa::communication_volume(B.grid, ng.g[1], tb);
+        vol += costa::communication_volume(ng.g[2], C.grid, 'N');
+        bool reordered = false;
+        perm = costa::optimal_reordering(vol, c->size, reordered);
+        if (!reordered) perm.clear();
+    }
     LayoutMultiplyState* st = nullptr;
-    int rc = get_state(c, dtype, m, n, k, steps, &st);
+    int rc = get_state(c, dtype, m, n, k, steps, perm, &st);
     if (rc != COSMA_B200_OK) return rc;
 
     std::string key;

@@ -334,6 +334,61 @@ def _worker(rank, world, port, nprow, npcol, q):
             for case in TRAN_CASES:
                 ok.append(_pxtran_case(comm, gr, gc2 if op == "N" else gr, case, dtype, op, nprow, npcol, "R", "C" if op == "N" else "R", host, gather))
     gr.destroy(); gc2.destroy()
+    # (4) multiply_using_layout across ranks: (a) random layouts with random owners; (b) COSMA's own layout with the rank
+    # labels reversed -- the relabelling must find the permutation, so that no element leaves its GPU
+    from cosma_b200 import planning
+
+    def own_blocks_equal(D, dev, want):
+        got = dev.download()
+        h = D
+        res = []
+        for bi in range(len(h.rowsplit) - 1):
+            for bj in range(len(h.colsplit) - 1):
+                if h.owners[bi, bj] == rank:
+                    sl = (slice(h.rowsplit[bi], h.rowsplit[bi + 1]), slice(h.colsplit[bj], h.colsplit[bj + 1]))
+                    res.append(bool(np.array_equal(got[sl], want[sl].astype(got.dtype))))
+        return all(res)
+
+    for trial, (dtype, ta, tb, m, n, k, alpha, beta) in enumerate((("d", "N", "N", 96, 80, 64, 1.0, 0.0), ("z", "C", "N", 70, 90, 50, 2.0, 1.0),
+                                                                   ("s", "N", "T", 128, 64, 96, 1.0, -1.0), ("c", "T", "C", 60, 60, 60, 1.0, 0.0))):
+        rng = np.random.default_rng(900 + trial)  # same on every rank
+        A = sim.random_values(rng, (m, k) if ta == "N" else (k, m), dtype)
+        B = sim.random_values(rng, (k, n) if tb == "N" else (n, k), dtype)
+        C = sim.random_values(rng, (m, n), dtype)
+        dA, dB, dC = (_rand_dist(rng, X.shape[0], X.shape[1], world, dtype, "C") for X in (A, B, C))
+        dA.scatter(A); dB.scatter(B); dC.scatter(C if beta != 0.0 else np.full_like(C, np.nan))
+        gA, gB, gC = DeviceDist(dA), DeviceDist(dB), DeviceDist(dC)
+        costa.multiply_using_layout(comm, dtype, ta, tb, alpha, gA.layout(rank), gB.layout(rank), beta, gC.layout(rank))
+        torch.cuda.synchronize()
+        wide = np.complex128 if dtype in "zc" else np.float64
+        want = alpha * (sim.apply_op(A, ta).astype(wide) @ sim.apply_op(B, tb).astype(wide)) + (beta * C.astype(wide) if beta != 0.0 else 0)
+        ok.append(own_blocks_equal(dC, gC, want))
+    m = n = k = 640  # every split keeps the local dimensions above COSMA_MIN_LOCAL_DIMENSION (200)
+    steps, P_used, _ = planning.strategy(m, n, k, world)
+    sigma = [world - 1 - r for r in range(world)]
+    mats = {}
+    rng = np.random.default_rng(4242)
+    for label, (rows, cols) in (("A", (m, k)), ("B", (k, n)), ("C", (m, n))):
+        per_rank = planning.mapper_layout(label, m, n, k, world, steps)
+        rs = sorted({b[0] for bl in per_rank for b in bl} | {rows})
+        cs = sorted({b[2] for bl in per_rank for b in bl} | {cols})
+        owners = np.zeros((len(rs) - 1, len(cs) - 1), dtype=np.int32)
+        for r, bl in enumerate(per_rank):
+            for (r0, r1, c0, c1) in bl:
+                for bi in range(len(rs) - 1):
+                    for bj in range(len(cs) - 1):
+                        if r0 <= rs[bi] <= r1 and c0 <= cs[bj] <= c1:
+                            owners[bi, bj] = sigma[r]
+        D = sim.DistMatrix(rs, cs, owners, world, "d", "C")
+        G = sim.random_values(rng, (rows, cols), "d")
+        D.scatter(G if label != "C" else np.full_like(G, np.nan))
+        mats[label] = (D, DeviceDist(D), G)
+    costa.multiply_using_layout(comm, "d", "N", "N", 1.0, mats["A"][1].layout(rank), mats["B"][1].layout(rank), 0.0, mats["C"][1].layout(rank))
+    torch.cuda.synchronize()
+    st = costa.last_layout_multiply_stats(comm)
+    ok.append(own_blocks_equal(mats["C"][0], mats["C"][1], mats["A"][2] @ mats["B"][2]))
+    if P_used == world and os.environ.get("COSMA_B200_REORDER_RANKS", "ON").upper() != "OFF":
+        ok.append(st["in_remote_elements"] == 0 and st["out_remote_elements"] == 0 and st["in_local_elements"] > 0)
     t = torch.tensor([1 if all(ok) else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

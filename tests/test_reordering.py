@@ -121,3 +121,34 @@ def test_relabelling_recovers_a_permuted_block_cyclic_layout(lib):
     kept = _kept_in_place(vol, perm)
     direct = int(np.trace(vol))
     assert kept >= direct and flag
+
+
+@pytest.mark.parametrize("world", [2, 4, 8, 6])
+def test_relabelling_finds_cosma_layout_with_reversed_ranks(lib, world):
+    """The case multiply_using_layout meets when the caller's layout IS COSMA's native layout up to a renumbering of the ranks
+    (reference multiply.cpp:136-152): the volume graph summed over A, B, C puts everything on the pairs (r, sigma(r)), and the
+    matching returns sigma -- after which every element is already in place."""
+    from cosma_b200 import planning
+    m = n = k = 640  # every split keeps the local dimensions above COSMA_MIN_LOCAL_DIMENSION (200)
+    steps, P_used, _ = planning.strategy(m, n, k, world)
+    assert P_used == world
+    sigma = [world - 1 - r for r in range(world)]
+    total = np.zeros((world, world), dtype=np.int64)
+    for label, (rows, cols) in (("A", (m, k)), ("B", (k, n)), ("C", (m, n))):
+        per_rank = planning.mapper_layout(label, m, n, k, world, steps)
+        rs = np.array(sorted({b[0] for bl in per_rank for b in bl} | {rows}), dtype=np.int32)
+        cs = np.array(sorted({b[2] for bl in per_rank for b in bl} | {cols}), dtype=np.int32)
+        native = np.zeros((len(rs) - 1, len(cs) - 1), dtype=np.int32)
+        for r, bl in enumerate(per_rank):
+            for (r0, r1, c0, c1) in bl:
+                for bi in range(len(rs) - 1):
+                    for bj in range(len(cs) - 1):
+                        if r0 <= rs[bi] <= r1 and c0 <= cs[bj] <= c1:
+                            native[bi, bj] = r
+        user = np.array([sigma[r] for r in native.reshape(-1)], dtype=np.int32)
+        a, b = (rs, cs, user), (rs, cs, native.reshape(-1).copy())
+        total += _volume(lib.cosma_b200_comm_volume, a, b, "N", world) if label != "C" else _volume(lib.cosma_b200_comm_volume, b, a, "N", world)
+    assert int(np.trace(total)) == 0 or world % 2 == 1
+    perm, flag = _reorder(lib.cosma_b200_optimal_reordering, total)
+    assert flag and list(perm) == sigma
+    assert _kept_in_place(total, perm) == 3 * m * n
