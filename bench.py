@@ -287,10 +287,12 @@ def main():
 
     # roofline of the dominant kernel (the DMMA GEMM): algorithmic flops per launch / average launch duration
     peak, peak_src = fp64_peak()
+    collectives = None
     if world == 1:
         kern_ms = sum(step_ms) / len(step_ms)
     else:
         kern_ms = job.mean_gemm_ms()
+        collectives = job.collectives()
     achieved = flops_per_kernel / (kern_ms * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "kernel": "gemm_f64_sm100_kernel (FP64 DMMA.8x8x4 pipe)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -344,6 +346,8 @@ def main():
                            "l2": "inputs larger than L2 (A+B+C = %.1f GB per job vs 126 MB L2)" % (8e-9 * (m * k + k * n + m * n)),
                            "fp64_peak_per_gpu_tflops": peak, "frac_of_fp64_peak": value / (peak * world)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if collectives is not None:
+            line["collectives"] = collectives  # rank 0's allgather / reduce-scatter device time and bus bandwidth in the last timed step
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

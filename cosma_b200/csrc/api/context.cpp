@@ -84,9 +84,11 @@ void cosma_context<Scalar>::register_state(MPI_Comm comm, const Strategy strateg
         plan_ = nullptr;
     }
     const std::string steps = strategy.to_string();
+    b200::trace(("register_state: plan for [" + steps + "]").c_str());
     b200::check(cosma_b200_plan_create_for_strategy(handle, rank, size, strategy.m, strategy.n, strategy.k, static_cast<int>(strategy.P), steps.c_str(),
                                                     b200::type_code<Scalar>::value, &plan_),
                 "cosma_context::register_state (plan)");
+    b200::trace("register_state: plan ready");
     prev_strategy = strategy;
     prev_comm_key = key;
     if (output && rank == 0) std::cout << "cosma_b200 plan for strategy [" << steps << "] on " << size << " rank(s)" << std::endl;

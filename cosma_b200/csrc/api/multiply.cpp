@@ -23,9 +23,12 @@ void multiply(cosma_context<Scalar>* ctx, CosmaMatrix<Scalar>& A, CosmaMatrix<Sc
     double a2[2], b2[2];
     b200::to_pair(alpha, a2);
     b200::to_pair(beta, b2);
+    b200::trace("multiply: queue");
     b200::check(cosma_b200_multiply_host(ctx->plan(), a2, b2, A.matrix_pointer(), B.matrix_pointer(), C.matrix_pointer(), ctx->stream()),
                 "cosma::multiply");
+    b200::trace("multiply: synchronize");
     b200::check(cosma_b200_stream_synchronize(ctx->stream()), "cosma::multiply (synchronize)");
+    b200::trace("multiply: done");
 }
 
 template <typename Scalar>

@@ -1,6 +1,7 @@
 #include <cosma/b200_runtime.hpp>
 #include <cosma/environment_variables.hpp>
 
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -12,6 +13,17 @@ void check(int status, const char* what) {
     if (status == COSMA_B200_OK) return;
     const char* msg = cosma_b200_last_error();
     throw std::runtime_error(std::string(what) + " failed (status " + std::to_string(status) + ")" + (msg && *msg ? std::string(": ") + msg : ""));
+}
+
+bool trace_enabled() {
+    static const bool on = get_bool_env_var("COSMA_B200_TRACE", false);
+    return on;
+}
+void trace(const char* what) {
+    if (!trace_enabled()) return;
+    const char* r = std::getenv("RANK");
+    std::fprintf(stderr, "[cosma rank %s] %s\n", r ? r : "0", what);
+    std::fflush(stderr);
 }
 
 void select_device() {
@@ -43,11 +55,14 @@ void* comm_handle(MPI_Comm comm) {
     MPI_Comm_size(comm, &size);
     uint8_t id[128] = {0};
     if (size > 1) {
+        trace("comm_handle: ncclGetUniqueId + broadcast");
         if (rank == 0) check(cosma_b200_nccl_unique_id(id), "cosma_b200_nccl_unique_id");
         MPI_Bcast(id, 128, MPI_BYTE, 0, comm);
+        trace("comm_handle: ncclCommInitRank");
     }
     void* handle = nullptr;
     check(cosma_b200_comm_create(rank, size, size > 1 ? id : nullptr, &handle), "cosma_b200_comm_create");
+    trace("comm_handle: communicator ready");
     g_comms[key] = handle;
     return handle;
 }

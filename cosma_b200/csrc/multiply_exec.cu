@@ -137,24 +137,23 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
     char* C = static_cast<char*>(C_);
     char* arenas[3] = {A, B, C};
     plan.last_launches = 0;
-    size_t n_gemm = 0;
-    for (const auto& op : plan.schedule.ops()) n_gemm += op.kind == cosma::OpKind::GEMM;
+    // with timing on, every op (GEMM, allgather, reduce) is bracketed by a pair of events: ev[2*i], ev[2*i+1] for op i
     if (plan.time_gemms) {
-        while (plan.ev.size() < 2 * n_gemm) {
+        while (plan.ev.size() < 2 * plan.schedule.ops().size()) {
             cudaEvent_t e;
             CUDA_TRY(cudaEventCreate(&e));
             plan.ev.push_back(e);
         }
     }
-    size_t gi = 0;
+    size_t oi = 0;
     for (const auto& op : plan.schedule.ops()) {
         int st = COSMA_B200_OK;
+        if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * oi], stream));
         switch (op.kind) {
             case cosma::OpKind::GEMM: {
                 double b[2] = {0.0, 0.0};
                 if (op.beta == cosma::BetaMode::ONE) b[0] = 1.0;
                 else if (op.beta == cosma::BetaMode::USER) { b[0] = beta[0]; b[1] = E == 2 ? beta[1] : 0.0; }
-                if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * gi], stream));
                 const int64_t lda = std::max(op.m, 1), ldb = std::max(op.k, 1), ldc = std::max(op.m, 1);
                 StreamGemmArgs g;
                 g.dtype = plan.dtype;
@@ -170,8 +169,6 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
                 }
                 int launches = 0;
                 st = stream_gemm(stream, g, &launches);
-                if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * gi + 1], stream));
-                ++gi;
                 plan.last_launches += launches;
                 break;
             }
@@ -183,6 +180,8 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
                 break;
         }
         if (st != COSMA_B200_OK) return st;
+        if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.ev[2 * oi + 1], stream));
+        ++oi;
     }
     return COSMA_B200_OK;
 }
@@ -445,12 +444,45 @@ int cosma_b200_plan_time_gemms(void* plan, int enable) {
 /* after a synchronised run with timing enabled: per-GEMM device milliseconds */
 int cosma_b200_plan_gemm_times(void* plan, float* out, int cap, int* n) {
     Plan* p = static_cast<Plan*>(plan);
+    const auto& ops = p->schedule.ops();
     int cnt = 0;
-    for (const auto& op : p->schedule.ops()) cnt += op.kind == cosma::OpKind::GEMM;
+    for (const auto& op : ops) cnt += op.kind == cosma::OpKind::GEMM;
     *n = cnt;
-    if (!p->time_gemms || static_cast<int>(p->ev.size()) < 2 * cnt) return COSMA_B200_INVALID_ARG;
-    for (int i = 0; i < cnt && i < cap; ++i)
-        if (cudaEventElapsedTime(&out[i], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+    if (!p->time_gemms || p->ev.size() < 2 * ops.size()) return COSMA_B200_INVALID_ARG;
+    int g = 0;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        if (ops[i].kind != cosma::OpKind::GEMM) continue;
+        if (g < cap && cudaEventElapsedTime(&out[g], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+        ++g;
+    }
+    return COSMA_B200_OK;
+}
+
+/* after a synchronised run with timing enabled: for every op of the schedule its kind (0 GEMM, 1 allgather, 2 reduce), device
+ * milliseconds, and for collectives the bytes this rank puts on / takes off the wire: (d-1)/d of the gathered (allgather) or
+ * reduced (reduce-scatter) buffer, d = ring size -- the "bus bandwidth" convention of SURVEY 8d. */
+int cosma_b200_plan_op_times(void* plan, int* kinds, float* ms, int64_t* wire_bytes, int cap, int* n) {
+    Plan* p = static_cast<Plan*>(plan);
+    if (!p || !n) return COSMA_B200_INVALID_ARG;
+    const auto& ops = p->schedule.ops();
+    *n = static_cast<int>(ops.size());
+    if (!p->time_gemms || p->ev.size() < 2 * ops.size()) return COSMA_B200_INVALID_ARG;
+    for (size_t i = 0; i < ops.size() && static_cast<int>(i) < cap; ++i) {
+        const auto& op = ops[i];
+        if (kinds) kinds[i] = op.kind == cosma::OpKind::GEMM ? 0 : (op.kind == cosma::OpKind::ALLGATHER ? 1 : 2);
+        if (ms && cudaEventElapsedTime(&ms[i], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+        if (wire_bytes) {
+            int64_t total = 0, mine = 0;
+            if (op.kind != cosma::OpKind::GEMM) {
+                for (size_t g = 0; g < op.piece.size(); ++g)
+                    for (auto v : op.piece[g]) {
+                        total += v;
+                        if (static_cast<int>(g) == op.my_pos) mine += v;
+                    }
+            }
+            wire_bytes[i] = (total - mine) * p->elem_bytes();
+        }
+    }
     return COSMA_B200_OK;
 }
 

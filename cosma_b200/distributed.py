@@ -193,6 +193,17 @@ class MultiplyPlan:
         _lib.check(st, "cosma_b200_plan_gemm_times")
         return list(out[:n.value])
 
+    def op_times(self):
+        """[(kind, ms, wire_bytes)] of the last synchronised run with timing on; kind in 'gemm' | 'allgather' | 'reduce'."""
+        n = ctypes.c_int(0)
+        cap = 65536
+        kinds, ms, wb = (ctypes.c_int * cap)(), (ctypes.c_float * cap)(), (ctypes.c_int64 * cap)()
+        self.lib.cosma_b200_plan_op_times.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float),
+                                                      ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        _lib.check(self.lib.cosma_b200_plan_op_times(self.handle, kinds, ms, wb, cap, ctypes.byref(n)), "cosma_b200_plan_op_times")
+        names = ("gemm", "allgather", "reduce")
+        return [(names[kinds[i]], ms[i], wb[i]) for i in range(min(n.value, cap))]
+
     def destroy(self):
         if self.handle:
             self.lib.cosma_b200_plan_destroy(self.handle)
@@ -246,6 +257,18 @@ class MultiplyJob:
     def mean_gemm_ms(self):
         t = self.plan.gemm_times_ms()
         return sum(t) / max(len(t), 1)
+
+    def collectives(self):
+        """Device time and bus bandwidth of the collectives of the last step on this rank (bytes = (d-1)/d of the
+        gathered / reduced buffer per rank)."""
+        out = {}
+        for kind in ("allgather", "reduce"):
+            sel = [(ms, wb) for k, ms, wb in self.plan.op_times() if k == kind]
+            if not sel:
+                continue
+            ms, wb = sum(x[0] for x in sel), sum(x[1] for x in sel)
+            out[kind] = {"count": len(sel), "ms": ms, "wire_bytes_per_rank": wb, "busbw_GBps": (wb / (ms * 1e-3) * 1e-9) if ms > 0 else None}
+        return out
 
     def e2e(self, reps):
         """Same multiply through the host-pointer entry point: pinned local A, B in, local C out, per step."""

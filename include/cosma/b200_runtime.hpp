@@ -13,6 +13,9 @@ namespace b200 {
 
 // throws std::runtime_error("<what>: <cosma_b200_last_error()>") unless status == COSMA_B200_OK
 void check(int status, const char* what);
+// COSMA_B200_TRACE=ON: one line per host-layer step on stderr ("[cosma rank r] ..."), for locating a stuck collective
+bool trace_enabled();
+void trace(const char* what);
 
 template <typename T> struct type_code;
 template <> struct type_code<float> { static constexpr char value = 's'; };

@@ -124,6 +124,9 @@ COSMA_B200_API int cosma_b200_multiply_host(void* plan, const double* alpha, con
 COSMA_B200_API int cosma_b200_plan_last_launches(void* plan);                  /* GEMM kernels launched by the last run */
 COSMA_B200_API int cosma_b200_plan_time_gemms(void* plan, int enable);         /* record CUDA events around each GEMM */
 COSMA_B200_API int cosma_b200_plan_gemm_times(void* plan, float* out_ms, int cap, int* n);
+/* With timing enabled, per op of the compiled schedule: kind (0 GEMM, 1 allgather, 2 reduce-scatter), device ms, and for the
+ * collectives the bytes this rank exchanges, (d-1)/d of the gathered / reduced buffer (ring size d). */
+COSMA_B200_API int cosma_b200_plan_op_times(void* plan, int* kinds, float* ms, int64_t* wire_bytes, int cap, int* n);
 
 /* ---- COSTA relayout (R3/R4 + exchange) ------------------------------------------------------------------
  * Layout description in the shape of the reference's C interface (src/cosma/cinterface.hpp:16-41: struct block,
