@@ -14,6 +14,7 @@
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <poll.h>
 #include <stdexcept>
 #include <string>
 #include <sys/socket.h>
@@ -345,6 +346,49 @@ void recv(group* g, void* buf, std::size_t bytes, int src, int tag) {
     std::lock_guard<std::recursive_mutex> lock(S().mu);
     if (src < 0 || src >= size(g)) fail("recv: source outside the communicator");
     raw_recv(g->members[src], g->gid, tag, buf, bytes);
+}
+
+int recv_any(group* g, void* buf, std::size_t bytes, int tag) {
+    check(g);
+    state_t& s = S();
+    std::lock_guard<std::recursive_mutex> lock(s.mu);
+    const int n = size(g);
+    for (;;) {
+        // anything already parked?
+        for (int i = 0; i < n; ++i) {
+            auto& q = s.parked[g->members[i]];
+            for (auto it = q.begin(); it != q.end(); ++it) {
+                if (it->h.gid == g->gid && it->h.tag == tag) {
+                    if (it->h.bytes != bytes) fail("message size mismatch");
+                    if (bytes) std::memcpy(buf, it->data.data(), bytes);
+                    q.erase(it);
+                    return i;
+                }
+            }
+        }
+        // wait until some member's socket has data, and park one frame from every readable socket
+        std::vector<pollfd> fds;
+        std::vector<int> who;
+        for (int i = 0; i < n; ++i) {
+            const int w = g->members[i];
+            if (w == s.world_rank || s.sock[w] < 0) continue;
+            fds.push_back(pollfd{s.sock[w], POLLIN, 0});
+            who.push_back(w);
+        }
+        if (fds.empty()) fail("recv_any: nobody to receive from");
+        if (::poll(fds.data(), fds.size(), -1) < 0) {
+            if (errno == EINTR) continue;
+            fail(std::string("poll: ") + std::strerror(errno));
+        }
+        for (size_t f = 0; f < fds.size(); ++f) {
+            if (!(fds[f].revents & (POLLIN | POLLHUP))) continue;
+            message m;
+            read_all(fds[f].fd, &m.h, sizeof(m.h));
+            m.data.resize(m.h.bytes);
+            if (m.h.bytes) read_all(fds[f].fd, m.data.data(), m.h.bytes);
+            s.parked[who[f]].push_back(std::move(m));
+        }
+    }
 }
 
 void bcast(group* g, void* buf, std::size_t bytes, int root) {

@@ -27,6 +27,7 @@ typedef int MPI_Status;
 #define MPI_COMM_NULL (static_cast<MPI_Comm>(nullptr))
 #define MPI_SUCCESS 0
 #define MPI_UNDEFINED (-32766)
+#define MPI_ANY_SOURCE (-2)
 #define MPI_STATUS_IGNORE (static_cast<MPI_Status*>(nullptr))
 #define MPI_STATUSES_IGNORE (static_cast<MPI_Status*>(nullptr))
 #define MPI_IN_PLACE (reinterpret_cast<void*>(-1))
@@ -75,8 +76,15 @@ inline int MPI_Send(const void* buf, int count, MPI_Datatype t, int dst, int tag
 inline int MPI_Ssend(const void* buf, int count, MPI_Datatype t, int dst, int tag, MPI_Comm c) {
     return MPI_Send(buf, count, t, dst, tag, c);
 }
-inline int MPI_Recv(void* buf, int count, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Status*) {
-    cosma::pg::recv(c, buf, cosma::pg::dtype_size(t) * static_cast<std::size_t>(count), src, tag);
+inline int MPI_Recv(void* buf, int count, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Status* status) {
+    const std::size_t bytes = cosma::pg::dtype_size(t) * static_cast<std::size_t>(count);
+    if (src == MPI_ANY_SOURCE) {
+        const int from = cosma::pg::recv_any(c, buf, bytes, tag);
+        if (status) *status = from;  // MPI_Status is the source rank in this subset
+    } else {
+        cosma::pg::recv(c, buf, bytes, src, tag);
+        if (status) *status = src;
+    }
     return MPI_SUCCESS;
 }
 inline int MPI_Gather(const void* send, int scount, MPI_Datatype st, void* recv, int, MPI_Datatype, int root, MPI_Comm c) {

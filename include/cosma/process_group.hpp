@@ -39,6 +39,8 @@ void barrier(group* g);
 void bcast(group* g, void* buf, std::size_t bytes, int root);
 void send(group* g, const void* buf, std::size_t bytes, int dst, int tag);
 void recv(group* g, void* buf, std::size_t bytes, int src, int tag);
+// receive from whichever member sends a message with this tag first (MPI_ANY_SOURCE); returns the sender's rank in g
+int recv_any(group* g, void* buf, std::size_t bytes, int tag);
 // recv must hold size(g) * bytes on the root
 void gather(group* g, const void* send, std::size_t bytes, void* recv, int root);
 void allgather(group* g, const void* send, std::size_t bytes, void* recv);

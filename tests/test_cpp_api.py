@@ -127,6 +127,50 @@ def test_compute_fails_loudly_without_gpu(host_libs):
     assert "no CPU fallback" in (out.stdout + out.stderr) or "cuda" in (out.stdout + out.stderr).lower()
 
 
+def _mock():
+    """tests/cpp/mock_b200.cpp -> libmock_b200.so: CPU stand-in for the C ABI entry points the host layer calls (test infrastructure)."""
+    src, out = os.path.join(CPP, "mock_b200.cpp"), os.path.join(BIN, "libmock_b200.so")
+    os.makedirs(BIN, exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(LIBDIR, "libcosma.so"))):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), src, "-o", out,
+                               "-L", LIBDIR, "-lcosma", "-Wl,-rpath," + LIBDIR])
+    return out
+
+
+def _run_on_mock(np_, argv, timeout=300):
+    from cosma_b200.launch import launch
+    code, outs = launch(np_, argv, timeout=timeout, capture=True, env_extra={"LD_PRELOAD": _mock()})
+    text = "\n".join("--- rank %d ---\n%s" % (r, o) for r, o in enumerate(outs))
+    assert code == 0, text[-6000:]
+    return outs[0]
+
+
+@pytest.mark.parametrize("name,np_", [("test_multiply", 2), ("test_multiply", 4), ("test_multiply", 7), ("test_multiply", 16),
+                                      ("test_multiply_using_layout", 2), ("test_multiply_using_layout", 6), ("test_pxgemm", 2), ("test_pxgemm", 8)])
+def test_cpp_programs_multirank_on_cpu(host_libs, oracle, name, np_):
+    """The C++ test programs on 2..16 RANKS without a GPU: the whole host layer is real (communicators, idle ranks, strategies,
+    coordinate maps, layout conversion, BLACS-lite, the MPI-name subset, the programs' own message protocols); only the C ABI entry
+    points underneath are replaced by a gather -> naive GEMM / dense relayout -> scatter stand-in (tests/cpp/mock_b200.cpp). At 16
+    ranks all 40 cases of the reference's tests/multiply.cpp run. Guards the GPU budget against protocol deadlocks."""
+    out = _run_on_mock(np_, [program(name)])
+    assert "failed = 0" in out, out[-4000:]
+    assert "checks passed (all ranks) = 0," not in out
+
+
+@pytest.mark.parametrize("np_,args", [(4, ["-m", "600", "-n", "500", "-k", "700", "-r", "2"]),
+                                      (5, ["-m", "300", "-n", "300", "-k", "300", "-r", "1", "-t", "zdouble"]),   # the strategy idles ranks
+                                      (6, ["-m", "640", "-n", "640", "-k", "640", "-s", "pm2,pk3", "-r", "1", "-t", "float"])])
+def test_cosma_miniapp_multirank_on_cpu(host_libs, np_, args):
+    out = _run_on_mock(np_, [program("cosma_miniapp")] + args)
+    assert "COSMA TIMES [ms] =" in out and "Strategy" in out, out
+
+
+def test_pxgemm_miniapp_multirank_on_cpu(host_libs):
+    out = _run_on_mock(6, [program("pxgemm_miniapp"), "-m", "200", "-n", "150", "-k", "100", "--block_a", "32,16", "--block_b", "8,8", "--block_c", "16,32",
+                           "--transpose", "TN", "-p", "2,3", "-r", "2", "--type", "zdouble"])
+    assert "COSMA TIMES [ms] =" in out and "grid 2 x 3" in out, out
+
+
 # ---- GPU --------------------------------------------------------------------------------------------------------------
 
 def _gpus():
