@@ -292,7 +292,10 @@ def main():
         kern_ms = sum(step_ms) / len(step_ms)
     else:
         kern_ms = job.mean_gemm_ms()
-        collectives = job.collectives()
+        try:
+            collectives = job.collectives()
+        except Exception as e:  # a reporting extra must never cost the bench line
+            collectives = {"error": str(e)}
     achieved = flops_per_kernel / (kern_ms * 1e-3) * 1e-12
     roofline = {"bound": "tensor", "kernel": "gemm_f64_sm100_kernel (FP64 DMMA.8x8x4 pipe)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
