@@ -15,9 +15,9 @@ void multiply(cosma_context<Scalar>* ctx, CosmaMatrix<Scalar>& A, CosmaMatrix<Sc
     if (comm == MPI_COMM_NULL) return;
     int rank = 0;
     MPI_Comm_rank(comm, &rank);
-    // plan creation splits NCCL communicators of the WHOLE comm, so idle ranks take part in it before returning
-    ctx->register_state(comm, strategy);
-    if (rank >= static_cast<int>(strategy.P)) return;  // multiply.cpp:258-260
+    if (rank >= static_cast<int>(strategy.P)) return;  // idle ranks take no part at all (multiply.cpp:258-260)
+    // everything below is collective over the first strategy.P ranks only, as in the reference (communicator.cpp:282-343)
+    ctx->register_state(b200::active_comm(comm, static_cast<int>(strategy.P)), strategy);
     if (A.m() != strategy.m || A.n() != strategy.k || B.m() != strategy.k || B.n() != strategy.n || C.m() != strategy.m || C.n() != strategy.n)
         throw std::runtime_error("cosma::multiply: matrix dimensions do not match the strategy");
     double a2[2], b2[2];

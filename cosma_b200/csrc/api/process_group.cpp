@@ -480,6 +480,23 @@ group* split(group* g, int color, int key) {
     return out;
 }
 
+group* create_group(group* g, const std::vector<int>& ranks, int tag) {
+    check(g);
+    std::uint64_t h = mix(g->gid, 0x6a09e667f3bcc908ull + static_cast<std::uint64_t>(static_cast<std::uint32_t>(tag)));
+    int my_pos = -1;
+    for (std::size_t i = 0; i < ranks.size(); ++i) {
+        if (ranks[i] < 0 || ranks[i] >= size(g)) fail("create_group: rank outside the parent communicator");
+        h = mix(h, static_cast<std::uint64_t>(ranks[i]) + 1);
+        if (ranks[i] == g->my_pos) my_pos = static_cast<int>(i);
+    }
+    if (my_pos < 0) return nullptr;
+    auto* out = new group;
+    out->gid = h;
+    out->my_pos = my_pos;
+    for (int r : ranks) out->members.push_back(g->members[r]);
+    return out;
+}
+
 group* dup(group* g) { return split(g, 0, rank(g)); }
 
 void free(group* g) {

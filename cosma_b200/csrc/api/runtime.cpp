@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <utility>
+#include <vector>
 #include <mutex>
 
 namespace cosma {
@@ -65,6 +67,34 @@ void* comm_handle(MPI_Comm comm) {
     trace("comm_handle: communicator ready");
     g_comms[key] = handle;
     return handle;
+}
+
+namespace {
+std::map<std::pair<unsigned long long, int>, MPI_Comm> g_active;
+}
+
+MPI_Comm active_comm(MPI_Comm comm, int P) {
+    int size = 1;
+    MPI_Comm_size(comm, &size);
+    if (P >= size) return comm;
+    const std::pair<unsigned long long, int> key(comm_key(comm), P);
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = g_active.find(key);
+        if (it != g_active.end()) return it->second;
+    }
+    MPI_Group all, first;
+    MPI_Comm_group(comm, &all);
+    std::vector<int> keep(P);
+    for (int i = 0; i < P; ++i) keep[i] = i;
+    MPI_Group_incl(all, P, keep.data(), &first);
+    MPI_Comm sub = MPI_COMM_NULL;
+    MPI_Comm_create_group(comm, first, /*tag=*/P, &sub);
+    MPI_Group_free(&all);
+    MPI_Group_free(&first);
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_active[key] = sub;
+    return sub;
 }
 
 void release_comm(MPI_Comm comm) {

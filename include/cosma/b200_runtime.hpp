@@ -35,6 +35,10 @@ void select_device();
 // ncclUniqueId and broadcasts it over `comm` as the reference does (src/cosma/gpu/nccl_utils.cpp:21-42) -- and cached by
 // communicator identity until release_comm / process exit (the reference caches per context, context.cpp:80-125).
 void* comm_handle(MPI_Comm comm);
+// The first P ranks of comm as a communicator of their own (comm itself when P == its size), created with
+// MPI_Comm_create_group -- collective over those P ranks only, like the reference's communicator (communicator.cpp:282-343)
+// -- and cached per (comm, P). Call it only on ranks < P.
+MPI_Comm active_comm(MPI_Comm comm, int P);
 void release_comm(MPI_Comm comm);
 void release_all_comms();
 

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #define COSMA_B200_MPI_COMPAT 1
 
@@ -105,6 +106,43 @@ inline int MPI_Allreduce(const void* send, void* recv, int count, MPI_Datatype t
 }
 inline int MPI_Comm_split(MPI_Comm c, int color, int key, MPI_Comm* out) {
     *out = cosma::pg::split(c, color == MPI_UNDEFINED ? -1 : color, key);
+    return MPI_SUCCESS;
+}
+// groups: ordered lists of ranks of the communicator they were taken from
+struct cosma_b200_mpi_group {
+    MPI_Comm parent;
+    std::vector<int> ranks;
+};
+typedef cosma_b200_mpi_group* MPI_Group;
+#define MPI_GROUP_NULL (static_cast<MPI_Group>(nullptr))
+inline int MPI_Comm_group(MPI_Comm c, MPI_Group* g) {
+    *g = new cosma_b200_mpi_group{c, {}};
+    for (int r = 0; r < cosma::pg::size(c); ++r) (*g)->ranks.push_back(r);
+    return MPI_SUCCESS;
+}
+inline int MPI_Group_incl(MPI_Group g, int n, const int* ranks, MPI_Group* out) {
+    *out = new cosma_b200_mpi_group{g->parent, {}};
+    for (int i = 0; i < n; ++i) (*out)->ranks.push_back(g->ranks[ranks[i]]);
+    return MPI_SUCCESS;
+}
+inline int MPI_Group_excl(MPI_Group g, int n, const int* ranks, MPI_Group* out) {
+    *out = new cosma_b200_mpi_group{g->parent, {}};
+    for (std::size_t i = 0; i < g->ranks.size(); ++i) {
+        bool drop = false;
+        for (int j = 0; j < n; ++j) drop = drop || ranks[j] == static_cast<int>(i);
+        if (!drop) (*out)->ranks.push_back(g->ranks[i]);
+    }
+    return MPI_SUCCESS;
+}
+inline int MPI_Group_size(MPI_Group g, int* n) { *n = static_cast<int>(g->ranks.size()); return MPI_SUCCESS; }
+inline int MPI_Group_free(MPI_Group* g) {
+    if (g) { delete *g; *g = MPI_GROUP_NULL; }
+    return MPI_SUCCESS;
+}
+// collective over the members of `g` only (the reference cuts the active ranks out of a communicator this way:
+// communicator.cpp:282-343, tests/multiply.cpp:7-36)
+inline int MPI_Comm_create_group(MPI_Comm c, MPI_Group g, int tag, MPI_Comm* out) {
+    *out = cosma::pg::create_group(c, g->ranks, tag);
     return MPI_SUCCESS;
 }
 inline int MPI_Comm_dup(MPI_Comm c, MPI_Comm* out) { *out = cosma::pg::dup(c); return MPI_SUCCESS; }

@@ -16,8 +16,7 @@ void multiply_using_layout(costa::grid_layout<Scalar>& A_layout, costa::grid_lay
                            Scalar alpha, Scalar beta, char transa, char transb, MPI_Comm comm);
 
 // Matrices in COSMA's native layout for `strategy`. Ranks >= strategy.P return at once; m, n or k == 0 returns at once
-// (multiply.cpp:252-260). Collective over the first strategy.P ranks of comm... and, the first time a (comm, strategy)
-// pair is seen, over all of comm (NCCL communicator creation).
+// (multiply.cpp:252-260). Collective over the first strategy.P ranks of comm only.
 template <typename Scalar>
 void multiply(CosmaMatrix<Scalar>& A, CosmaMatrix<Scalar>& B, CosmaMatrix<Scalar>& C, const Strategy& strategy, MPI_Comm comm, Scalar alpha,
               Scalar beta);

@@ -49,6 +49,10 @@ void allreduce(group* g, const void* send, void* recv, int count, dtype t, op o)
 
 // MPI_Comm_split: members with the same color form a group ordered by (key, old rank); color < 0 -> nullptr.
 group* split(group* g, int color, int key);
+// MPI_Comm_create_group: the listed ranks of g (in this order) form a new group. Collective over the LISTED ranks only -- in
+// fact purely local here: membership and identity follow from (g, ranks, tag), which every member passes identically.
+// Returns nullptr on a rank that is not listed.
+group* create_group(group* g, const std::vector<int>& ranks, int tag);
 group* dup(group* g);
 void free(group* g);  // the world group is never freed
 

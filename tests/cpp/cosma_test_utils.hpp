@@ -72,10 +72,17 @@ inline std::complex<float> make_value<std::complex<float>>(std::mt19937& gen) {
 
 // the first new_P ranks of comm (the reference builds it with MPI groups, tests/multiply.cpp:7-36)
 inline MPI_Comm subcommunicator(int new_P, MPI_Comm comm = MPI_COMM_WORLD) {
-    int rank = 0;
-    MPI_Comm_rank(comm, &rank);
+    int P = 0;
+    MPI_Comm_size(comm, &P);
+    MPI_Group all, kept;
+    MPI_Comm_group(comm, &all);
+    std::vector<int> excluded;
+    for (int i = new_P; i < P; ++i) excluded.push_back(i);
+    MPI_Group_excl(all, static_cast<int>(excluded.size()), excluded.data(), &kept);
     MPI_Comm out = MPI_COMM_NULL;
-    MPI_Comm_split(comm, rank < new_P ? 0 : MPI_UNDEFINED, rank, &out);
+    MPI_Comm_create_group(comm, kept, 0, &out);  // MPI_COMM_NULL on the excluded ranks
+    MPI_Group_free(&all);
+    MPI_Group_free(&kept);
     return out;
 }
 

@@ -100,6 +100,17 @@ int main(int argc, char** argv) {
         }
         MPI_Barrier(MPI_COMM_WORLD);
     }
+    // idle ranks: every rank of the world calls multiply() with the WORLD communicator and an automatic strategy that uses fewer
+    // ranks than the world has (small matrices; reference miniapp/cosma_miniapp.cpp:35-81, multiply.cpp:258-260). Ranks >= P own
+    // nothing, return at once and take no part in any collective.
+    {
+        Strategy small(260, 240, 220, world);
+        auto ctx = cosma::make_context<double>();
+        const bool ok = testutil::test_cosma<double>(small, ctx, MPI_COMM_WORLD, 1e-8, 1000);
+        if (rank == 0) std::printf("idle ranks: strategy uses %d of %d ranks: %d\n", static_cast<int>(small.P), world, ok);
+        CHECK_TRUE(ok);
+        MPI_Barrier(MPI_COMM_WORLD);
+    }
     cosma::b200::release_all_comms();
     const int rc = check::finish("test_multiply");
     MPI_Finalize();
