@@ -11,6 +11,8 @@
 #include <cosma/prefixed_pxgemm.h>
 #include <cosma/pxgemm.h>
 
+#include <cstdlib>
+#include <fstream>
 #include <limits>
 
 using testutil::real_of;
@@ -31,11 +33,12 @@ struct dist_matrix {
     int M, N, mb, nb, rsrc, csrc, lld, lrows, lcols;
     int desc[9];
     std::vector<T> local;
-    dist_matrix(int ctxt, int M_, int N_, int mb_, int nb_, int rsrc_, int csrc_, int nprow, int npcol, int myrow, int mycol)
+    // lld_ <= 0: local rows + 2 rows of padding
+    dist_matrix(int ctxt, int M_, int N_, int mb_, int nb_, int rsrc_, int csrc_, int nprow, int npcol, int myrow, int mycol, int lld_ = 0)
         : M(M_), N(N_), mb(mb_), nb(nb_), rsrc(rsrc_), csrc(csrc_) {
         lrows = myrow >= 0 ? numroc_(&M, &mb, &myrow, &rsrc, &nprow) : 0;
         lcols = myrow >= 0 ? numroc_(&N, &nb, &mycol, &csrc, &npcol) : 0;
-        lld = std::max(1, lrows) + 2;
+        lld = lld_ > 0 ? std::max(lld_, std::max(1, lrows)) : std::max(1, lrows) + 2;
         int info = 0;
         descinit_(desc, &M, &N, &mb, &nb, &rsrc, &csrc, &ctxt, &lld, &info);
         local.assign(static_cast<size_t>(lld) * std::max(1, lcols), T{-555});
@@ -71,17 +74,41 @@ struct px_case {
     double alpha, beta;
 };
 
+// every argument of a p?gemm call spelled out: the parameter set of the reference's tests/pdgemm.cpp (cosma::pxgemm_params,
+// src/cosma/pxgemm_params.hpp:227-290)
+struct full_case {
+    int ma, na, mb, nb, mc, nc;              // global matrix sizes
+    int bma, bna, bmb, bnb, bmc, bnc;        // block sizes
+    int ia, ja, ib, jb, ic, jc;              // sub-matrix origins (1-based)
+    int m, n, k;
+    char ta, tb;
+    double alpha, beta;
+    int lld_a, lld_b, lld_c;                 // <= 0: chosen by the test
+    int p_rows, p_cols;
+    char order;
+    int src_ma, src_na, src_mb, src_nb, src_mc, src_nc;
+};
+
+static full_case expand(const px_case& pc, int nprow, int npcol, char order) {
+    const bool tA = pc.ta != 'N', tB = pc.tb != 'N';
+    const int am = tA ? pc.k : pc.m, an = tA ? pc.m : pc.k, bm = tB ? pc.n : pc.k, bn = tB ? pc.k : pc.n;
+    const int rs = pc.src ? nprow - 1 : 0, cs = pc.src ? npcol - 1 : 0;
+    return full_case{am + pc.ia - 1 + pc.extra, an + pc.ja - 1 + pc.extra, bm + pc.ib - 1 + pc.extra, bn + pc.jb - 1 + pc.extra,
+                     pc.m + pc.ic - 1 + pc.extra, pc.n + pc.jc - 1 + pc.extra,
+                     pc.a_blk[0], pc.a_blk[1], pc.b_blk[0], pc.b_blk[1], pc.c_blk[0], pc.c_blk[1],
+                     pc.ia, pc.ja, pc.ib, pc.jb, pc.ic, pc.jc, pc.m, pc.n, pc.k, pc.ta, pc.tb, pc.alpha, pc.beta, 0, 0, 0, nprow, npcol, order,
+                     rs, cs, 0, cs, rs, 0};
+}
+
 template <typename T>
-static void run_case(int ctxt, const px_case& pc, int variant) {
+static void run_case(int ctxt, const full_case& pc, int variant) {
     using R = typename real_of<T>::type;
     int nprow, npcol, myrow, mycol;
     cosma::blacs::Cblacs_gridinfo(ctxt, &nprow, &npcol, &myrow, &mycol);
     const bool tA = pc.ta != 'N', tB = pc.tb != 'N';
-    const int am = tA ? pc.k : pc.m, an = tA ? pc.m : pc.k, bm = tB ? pc.n : pc.k, bn = tB ? pc.k : pc.n;
-    const int rs = pc.src ? nprow - 1 : 0, cs = pc.src ? npcol - 1 : 0;
-    dist_matrix<T> A(ctxt, am + pc.ia - 1 + pc.extra, an + pc.ja - 1 + pc.extra, pc.a_blk[0], pc.a_blk[1], rs, cs, nprow, npcol, myrow, mycol);
-    dist_matrix<T> B(ctxt, bm + pc.ib - 1 + pc.extra, bn + pc.jb - 1 + pc.extra, pc.b_blk[0], pc.b_blk[1], 0, cs, nprow, npcol, myrow, mycol);
-    dist_matrix<T> C(ctxt, pc.m + pc.ic - 1 + pc.extra, pc.n + pc.jc - 1 + pc.extra, pc.c_blk[0], pc.c_blk[1], rs, 0, nprow, npcol, myrow, mycol);
+    dist_matrix<T> A(ctxt, pc.ma, pc.na, pc.bma, pc.bna, pc.src_ma, pc.src_na, nprow, npcol, myrow, mycol, pc.lld_a);
+    dist_matrix<T> B(ctxt, pc.mb, pc.nb, pc.bmb, pc.bnb, pc.src_mb, pc.src_nb, nprow, npcol, myrow, mycol, pc.lld_b);
+    dist_matrix<T> C(ctxt, pc.mc, pc.nc, pc.bmc, pc.bnc, pc.src_mc, pc.src_nc, nprow, npcol, myrow, mycol, pc.lld_c);
     const T alpha = static_cast<T>(pc.alpha), beta = static_cast<T>(pc.beta);
     const T nan = T(std::numeric_limits<R>::quiet_NaN());
     auto in_sub_c = [&](int gi, int gj) { return gi >= pc.ic - 1 && gi < pc.ic - 1 + pc.m && gj >= pc.jc - 1 && gj < pc.jc - 1 + pc.n; };
@@ -110,7 +137,7 @@ static void run_case(int ctxt, const px_case& pc, int variant) {
                            reinterpret_cast<R*>(C.local.data()), &pc.ic, &pc.jc, C.desc);
 
     bool ok = true, untouched = true, pad = true;
-    const double tol = sizeof(R) == 4 ? 2e-4 : 1e-11;
+    const double tol = (sizeof(R) == 4 ? 2e-4 : 1e-11) * std::max(1.0, pc.k / 256.0);  // entries are O(1): errors grow with k
     if (myrow >= 0) {
         for (int lj = 0; lj < C.lcols; ++lj) {
             for (int li = 0; li < C.lld; ++li) {
@@ -151,14 +178,38 @@ int main(int argc, char** argv) {
         cosma::blacs::Cblacs_gridinit(&ctxt, &ord, nprow, npcol);
         int v = 0;
         for (const auto& pc : cases) {
-            run_case<double>(ctxt, pc, v);
-            run_case<std::complex<double>>(ctxt, pc, v);
-            run_case<float>(ctxt, pc, v);
-            run_case<std::complex<float>>(ctxt, pc, v);
+            const full_case fc = expand(pc, nprow, npcol, order);
+            run_case<double>(ctxt, fc, v);
+            run_case<std::complex<double>>(ctxt, fc, v);
+            run_case<float>(ctxt, fc, v);
+            run_case<std::complex<float>>(ctxt, fc, v);
             ++v;
         }
         cosma::pxgemm_release_grids();
         cosma::blacs::Cblacs_gridexit(ctxt);
+    }
+    // the reference's own 50 parameter sets (tests/pdgemm.cpp, extracted by tests/golden/make_pdgemm_cases.py): each on the grid
+    // it names, made of the first p_rows x p_cols ranks of the job; sets needing more ranks than the job has are skipped
+    {
+        const char* env = std::getenv("COSMA_B200_PDGEMM_CASES");
+        std::ifstream in(env && *env ? env : "tests/golden/pdgemm_cases.txt");
+        full_case fc;
+        int v = 0, ran = 0;
+        while (in >> fc.ma >> fc.na >> fc.mb >> fc.nb >> fc.mc >> fc.nc >> fc.bma >> fc.bna >> fc.bmb >> fc.bnb >> fc.bmc >> fc.bnc >> fc.ia >> fc.ja >>
+               fc.ib >> fc.jb >> fc.ic >> fc.jc >> fc.m >> fc.n >> fc.k >> fc.ta >> fc.tb >> fc.alpha >> fc.beta >> fc.lld_a >> fc.lld_b >> fc.lld_c >>
+               fc.p_rows >> fc.p_cols >> fc.order >> fc.src_ma >> fc.src_na >> fc.src_mb >> fc.src_nb >> fc.src_mc >> fc.src_nc) {
+            ++v;
+            if (fc.p_rows * fc.p_cols > P) { ++check::skipped(); continue; }
+            int ctxt = 0;
+            cosma::blacs::Cblacs_get(0, 0, &ctxt);
+            cosma::blacs::Cblacs_gridinit(&ctxt, &fc.order, fc.p_rows, fc.p_cols);
+            run_case<double>(ctxt, fc, v);
+            if (fc.k <= 2000) run_case<std::complex<float>>(ctxt, fc, v);
+            cosma::pxgemm_release_grids();
+            cosma::blacs::Cblacs_gridexit(ctxt);
+            ++ran;
+        }
+        if (rank == 0) std::printf("reference pdgemm parameter sets: %d read, %d run on %d rank(s)\n", v, ran, P);
     }
     cosma::b200::release_all_comms();
     const int rc = check::finish("test_pxgemm");

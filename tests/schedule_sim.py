@@ -73,6 +73,23 @@ def simulate(m, n, k, P, steps, alpha=1.0, beta=0.0, dtype="d", seed=0, ints=Tru
                 got = fill_local_from_global(pl, label, bufs[x], full)
                 assert got == pl.initial_elements[x]
         arenas.append(bufs)
+    run_schedules(plans, arenas, alpha, beta)
+    got = np.zeros((m, n), dtype=npdt)
+    for r in range(P_used):
+        gather_local_to_global(plans[r], "C", arenas[r][2], got)
+    want = alpha * (Ag @ Bg) + beta * Cg
+    if local_c is not None:
+        local_c.extend(arenas[r][2][:plans[r].initial_elements[2]].copy() if r < P_used else None for r in range(P))
+    for pl in plans:
+        pl.destroy()
+    return got, want, P_used
+
+
+def run_schedules(plans, arenas, alpha, beta):
+    """Executes the compiled schedules of all ranks in lock-step on the given arenas ([rank][matrix] numpy buffers whose first
+    initial_elements hold the rank's local matrix)."""
+    P = len(plans)
+    P_used = plans[0].P_used
     progs = [pl.ops() if r < P_used else [] for r, pl in enumerate(plans)]
     pc = [0] * P
     while any(pc[r] < len(progs[r]) for r in range(P)):
@@ -116,12 +133,3 @@ def simulate(m, n, k, P, steps, alpha=1.0, beta=0.0, dtype="d", seed=0, ints=Tru
                 pc[q] += 1
             progressed = True
         assert progressed, "schedule deadlock: %s" % [(r, pc[r], len(progs[r])) for r in range(P)]
-    got = np.zeros((m, n), dtype=npdt)
-    for r in range(P_used):
-        gather_local_to_global(plans[r], "C", arenas[r][2], got)
-    want = alpha * (Ag @ Bg) + beta * Cg
-    if local_c is not None:
-        local_c.extend(arenas[r][2][:plans[r].initial_elements[2]].copy() if r < P_used else None for r in range(P))
-    for pl in plans:
-        pl.destroy()
-    return got, want, P_used

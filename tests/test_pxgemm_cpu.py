@@ -1,0 +1,123 @@
+"""Our p?gemm pipeline executed END TO END ON THE CPU, all ranks in lock-step, on the 50 parameter sets of the reference's
+tests/pdgemm.cpp (tests/golden/pdgemm_cases.json) -- with the very plans the GPU executes:
+
+    block-cyclic sub(A), sub(B)  --costa transform plan (op = transa / transb, alpha 1, beta 0)-->  COSMA's native layout
+    compiled multiply schedule (allgather / GEMM / reduce ops on the arenas, alpha 1, beta 0)
+    native C  --costa transform plan (alpha, beta)-->  block-cyclic sub(C)
+
+(the three phases of cosma_b200_p?gemm, csrc/layout_multiply.cu, reference cosma_pxgemm.cpp:16-388). The transform plans come from
+cosma_b200_transform_plan_create (planning only, one per rank), the schedules from cosma_b200_plan_create; tests/costa_sim.py and
+tests/schedule_sim.py interpret them with numpy. Results are compared with the dense definition on integer-valued matrices
+(exact) -- the same expectation the unmodified reference meets on these sets in tests/test_ref_scalapack_cpu.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import costa_sim as sim
+import schedule_sim
+from cosma_b200 import costa
+from cosma_b200.distributed import MultiplyPlan
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _cases():
+    with open(os.path.join(HERE, "golden", "pdgemm_cases.json")) as f:
+        return json.load(f)["cases"]
+
+
+def _native_layouts(plans, label, arenas, x, shape, P):
+    """COSMA's native layout of one matrix as per-rank costa layouts whose blocks point into the ranks' arenas."""
+    P_used = plans[0].P_used
+    per_rank = [plans[0].local_blocks(label, r) for r in range(P)]
+    rs = sorted({b[0] for bl in per_rank for b in bl} | {shape[0]})
+    cs = sorted({b[2] for bl in per_rank for b in bl} | {shape[1]})
+    owners = np.zeros((len(rs) - 1, len(cs) - 1), dtype=np.int32)
+    for r, bl in enumerate(per_rank):
+        for (r0, r1, c0, c1) in bl:
+            owners[rs.index(r0), cs.index(c0)] = r
+    layouts = []
+    for r in range(P):
+        blocks, pos = [], 0
+        for (r0, r1, c0, c1) in (per_rank[r] if r < P_used else []):
+            nr, nc = r1 - r0 + 1, c1 - c0 + 1
+            blocks.append((rs.index(r0), cs.index(c0), arenas[r][x].ctypes.data + pos * 8, nr))
+            pos += nr * nc
+        layouts.append(costa.custom_layout(rs, cs, owners, blocks, "C"))
+    return layouts
+
+
+def run_pdgemm_on_cpu(oracle, c, seed):
+    nprow, npcol, order, P = c["p_rows"], c["p_cols"], c["order"], c["p_rows"] * c["p_cols"]
+    m, n, k, ta, tb, alpha, beta = c["m"], c["n"], c["k"], c["ta"], c["tb"], c["alpha"], c["beta"]
+    subs = ((c["ia"], c["ja"]), (c["ib"], c["jb"]), (c["ic"], c["jc"]))
+    shapes = [(c["ma"], c["na"]), (c["mb"], c["nb"]), (c["mc"], c["nc"])]
+    blks = [(c["bma"], c["bna"]), (c["bmb"], c["bnb"]), (c["bmc"], c["bnc"])]
+    srcs = [(c["src_ma"], c["src_na"]), (c["src_mb"], c["src_nb"]), (c["src_mc"], c["src_nc"])]
+    am, an = (m, k) if ta == "N" else (k, m)
+    bm, bn = (k, n) if tb == "N" else (n, k)
+    subdims = [(am, an), (bm, bn), (m, n)]
+    rng = np.random.default_rng(seed)
+    G = [sim.random_values(rng, s, "d") for s in shapes]
+    want = G[2].copy()
+    (ia, ja), (ib, jb), (ic, jc) = subs
+    As = sim.apply_op(G[0][ia - 1:ia - 1 + am, ja - 1:ja - 1 + an], ta)
+    Bs = sim.apply_op(G[1][ib - 1:ib - 1 + bm, jb - 1:jb - 1 + bn], tb)
+    want[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = alpha * (As @ Bs) + (beta * G[2][ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] if beta != 0 else 0)
+    # the caller's block-cyclic local arrays (C poisoned with NaN inside sub(C) when beta == 0: it must not be read)
+    bc = [sim.BlockCyclic(s[0], s[1], b[0], b[1], nprow, npcol, order, r[0], r[1], lld_pad=1) for s, b, r in zip(shapes, blks, srcs)]
+    Cin = G[2].copy()
+    if beta == 0:
+        Cin[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = np.nan
+    locs = [[bc[x].scatter((G[0], G[1], Cin)[x], r) for r in range(P)] for x in range(3)]
+    user = [[costa.block_cyclic_layout(shapes[x][0], shapes[x][1], blks[x][0], blks[x][1], subs[x][0], subs[x][1], subdims[x][0], subdims[x][1],
+                                       nprow, npcol, order, srcs[x][0], srcs[x][1], locs[x][r].ctypes.data, bc[x].local_shape(r)[0], "C", r, 8)
+             for r in range(P)] for x in range(3)]
+    # phase 0: the multiply plans (automatic strategy, as p?gemm uses) and their arenas
+    plans = [MultiplyPlan(None, m, n, k, "", "d", rank=r, nranks=P, allocate=False) for r in range(P)]
+    arenas = [[np.zeros(max(pl.arena_elements[x], 1), dtype=np.float64) for x in range(3)] for pl in plans]
+    native = [_native_layouts(plans, "ABC"[x], arenas, x, ((m, k), (k, n), (m, n))[x], P) for x in range(3)]
+    # phase 1: relayout op(sub(A)), op(sub(B)) into the native layout -- one exchange, two transforms
+    tin = []
+    for r in range(P):
+        tp = costa.TransformPlan(None, "d", [(user[0][r], native[0][r], ta, 1.0, 0.0), (user[1][r], native[1][r], tb, 1.0, 0.0)], rank=r, nranks=P)
+        tin.append(tp.export()); tp.destroy()
+    sim.simulate(oracle, "d", tin, [(1.0, 0.0), (1.0, 0.0)])
+    # phase 2: the compiled schedule, alpha = 1, beta = 0
+    schedule_sim.run_schedules(plans, arenas, 1.0, 0.0)
+    # phase 3: native C -> sub(C) with the caller's alpha and beta
+    tout = []
+    for r in range(P):
+        tp = costa.TransformPlan(None, "d", [(native[2][r], user[2][r], "N", alpha, beta)], rank=r, nranks=P)
+        tout.append(tp.export()); tp.destroy()
+    sim.simulate(oracle, "d", tout, [(alpha, beta)])
+    strategy = plans[0].strategy
+    for pl in plans:
+        pl.destroy()
+    got = np.zeros_like(G[2])
+    for r in range(P):
+        bc[2].gather_into(got, locs[2][r], r)
+    return got, want, strategy
+
+
+@pytest.mark.parametrize("chunk", range(5))
+def test_pdgemm_parameter_sets_in_lock_step(lib, oracle, chunk):
+    cases = _cases()
+    ran = 0
+    for idx in range(chunk * 10, chunk * 10 + 10):
+        c = cases[idx]
+        if c["m"] == 0 or c["n"] == 0 or c["k"] == 0 or c["alpha"] == 0:
+            continue  # no product: p?gemm only scales sub(C) (corner cases of the BLAS standard; covered by the GPU tests)
+        got, want, strategy = run_pdgemm_on_cpu(oracle, c, 2000 + idx)
+        assert np.allclose(got, want, rtol=1e-14, atol=0), (idx, strategy, c)
+        assert not np.isnan(got).any()
+        ran += 1
+    assert ran >= 2
+
+
+def test_most_parameter_sets_have_a_product():
+    cases = _cases()
+    assert len(cases) == 50
+    assert sum(1 for c in cases if c["m"] and c["n"] and c["k"] and c["alpha"] != 0) >= 40

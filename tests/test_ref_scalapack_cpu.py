@@ -62,3 +62,48 @@ def test_reference_pxgemm_on_ranks(lib, refd, nprow, npcol, order, dtype):
         for r in range(P):
             bc[2].gather_into(got, outs[r], r)
         assert np.array_equal(got, want), case
+
+
+def _pdgemm_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pdgemm_cases.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("chunk", range(5))
+def test_reference_pdgemm_parameter_sets(lib, refd, chunk):
+    """The 50 parameter sets of the reference's tests/pdgemm.cpp (tests/golden/pdgemm_cases.json, extracted by make_pdgemm_cases.py),
+    run through the UNMODIFIED reference cosma::pxgemm on the grid each set names (1-16 minimpi ranks) and compared with the dense
+    definition on integer-valued matrices. The reference checks them against a vendor ScaLAPACK, absent here: this is what pins the
+    reference-with-stand-ins as the oracle of our p?gemm on exactly these cases (tests/cpp/test_pxgemm.cpp runs the same sets through
+    our C++ API; sub-matrix offsets, rectangular grids, k = 43417, m|n|k = 0, alpha = 0 and beta = 0 included)."""
+    cases = _pdgemm_cases()
+    assert len(cases) == 50
+    for idx in range(chunk * 10, chunk * 10 + 10):
+        c = cases[idx]
+        nprow, npcol, order, P = c["p_rows"], c["p_cols"], c["order"], c["p_rows"] * c["p_cols"]
+        rng = np.random.default_rng(1000 + idx)
+        shapes = [(c["ma"], c["na"]), (c["mb"], c["nb"]), (c["mc"], c["nc"])]
+        blks = [(c["bma"], c["bna"]), (c["bmb"], c["bnb"]), (c["bmc"], c["bnc"])]
+        srcs = [(c["src_ma"], c["src_na"]), (c["src_mb"], c["src_nb"]), (c["src_mc"], c["src_nc"])]
+        G = [sim.random_values(rng, s, "d") for s in shapes]
+        bc = [sim.BlockCyclic(s[0], s[1], b[0], b[1], nprow, npcol, order, r[0], r[1]) for s, b, r in zip(shapes, blks, srcs)]
+        m, n, k, ta, tb, alpha, beta = c["m"], c["n"], c["k"], c["ta"], c["tb"], c["alpha"], c["beta"]
+        (ia, ja), (ib, jb), (ic, jc) = (c["ia"], c["ja"]), (c["ib"], c["jb"]), (c["ic"], c["jc"])
+        am, an = (m, k) if ta == "N" else (k, m)
+        bm, bn = (k, n) if tb == "N" else (n, k)
+        want = G[2].copy()
+        if m and n:
+            As = sim.apply_op(G[0][ia - 1:ia - 1 + am, ja - 1:ja - 1 + an], ta)
+            Bs = sim.apply_op(G[1][ib - 1:ib - 1 + bm, jb - 1:jb - 1 + bn], tb)
+            sub = G[2][ic - 1:ic - 1 + m, jc - 1:jc - 1 + n]
+            want[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = (alpha * (As @ Bs) if k and alpha != 0 else 0) + (beta * sub if beta != 0 else 0)
+        locs = [[bc[x].scatter(G[x], r) for r in range(P)] for x in range(3)]
+        descs = [[bc[x].desc(r) for r in range(P)] for x in range(3)]
+        outs, _ = refd.ref_pxgemm_ranks("d", order, nprow, npcol, ta, tb, m, n, k, alpha, locs[0], ia, ja, descs[0], locs[1], ib, jb, descs[1], beta,
+                                        locs[2], ic, jc, descs[2])
+        got = np.zeros_like(G[2])
+        for r in range(P):
+            bc[2].gather_into(got, outs[r], r)
+        assert np.allclose(got, want, rtol=1e-14, atol=0), (idx, c)
