@@ -24,6 +24,7 @@ PROGRAMS = {
     "test_process_group": (os.path.join(CPP, "test_process_group.cpp"), [], False),
     "test_multiply": (os.path.join(CPP, "test_multiply.cpp"), [], True),
     "test_multiply_using_layout": (os.path.join(CPP, "test_multiply_using_layout.cpp"), [], True),
+    "test_costa_examples": (os.path.join(CPP, "test_costa_examples.cpp"), [], False),
     "test_pxgemm": (os.path.join(CPP, "test_pxgemm.cpp"), ["cosma_prefixed_pxgemm", "cosma_pxgemm", "cosma_pxgemm_cpp", "cosma_blacs_lite"], True),
     "cosma_miniapp": (os.path.join(ROOT, "miniapp", "cosma_miniapp.cpp"), [], False),
     "pxgemm_miniapp": (os.path.join(ROOT, "miniapp", "pxgemm_miniapp.cpp"), ["cosma_pxgemm_cpp", "cosma_blacs_lite"], False),
@@ -146,7 +147,8 @@ def _run_on_mock(np_, argv, timeout=300):
 
 
 @pytest.mark.parametrize("name,np_", [("test_multiply", 2), ("test_multiply", 4), ("test_multiply", 7), ("test_multiply", 16),
-                                      ("test_multiply_using_layout", 2), ("test_multiply_using_layout", 6), ("test_pxgemm", 2), ("test_pxgemm", 8)])
+                                      ("test_multiply_using_layout", 2), ("test_multiply_using_layout", 6), ("test_pxgemm", 2), ("test_pxgemm", 8),
+                                      ("test_costa_examples", 4)])
 def test_cpp_programs_multirank_on_cpu(host_libs, oracle, name, np_):
     """The C++ test programs on 2..16 RANKS without a GPU: the whole host layer is real (communicators, idle ranks, strategies,
     coordinate maps, layout conversion, BLACS-lite, the MPI-name subset, the programs' own message protocols); only the C ABI entry
@@ -191,10 +193,12 @@ def _skip_unless_ranks(np_):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["test_multiply", "test_multiply_using_layout", "test_pxgemm"])
+@pytest.mark.parametrize("name", ["test_multiply", "test_multiply_using_layout", "test_pxgemm", "test_costa_examples"])
 @pytest.mark.parametrize("np_", [1, 2, 4, 8])
 def test_cpp_program(host_libs, oracle, name, np_):
     _skip_unless_ranks(np_)
+    if name == "test_costa_examples" and np_ != 4:
+        pytest.skip("the COSTA examples are written for 4 ranks")
     out = run_ranks(np_, [program(name)], timeout=240)
     assert "failed = 0" in out, out[-4000:]
     assert "checks passed (all ranks) = 0," not in out, out[-2000:]
