@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY -- a CPU stand-in for the entry points of libcosma_b200.so that the C++ host layer calls,
-// LD_PRELOADed in front of the real library by tests/test_cpp_api.py::test_cpp_programs_multirank_on_cpu. It lets the whole host
+// LD_PRELOADed in front of the real library by tests/test_z_cpp_api.py::test_cpp_programs_multirank_on_cpu. It lets the whole host
 // layer (cosma::multiply / CosmaMatrix / multiply_using_layout, costa::transform, the C interface, cosma::pxgemm + BLACS-lite,
 // the MPI-name subset, the test programs themselves) run on 1..16 RANKS on a box without GPUs: rank bookkeeping, idle ranks,
 // strategies, coordinate maps, layout conversions and message protocols are all real; only the arithmetic is replaced by
