@@ -55,7 +55,10 @@ HOST_LIBS = [
      [os.path.join("api", f) for f in ("process_group.cpp", "runtime.cpp", "context.cpp", "matrix.cpp", "multiply.cpp", "costa_api.cpp",
                                        "cinterface.cpp")], ["cosma_b200"]),
     ("libcosma_blacs_lite.so", [os.path.join("api", "blacs_lite.cpp")], ["cosma"]),
-    ("libcosma_pxgemm_cpp.so", [os.path.join("api", f) for f in ("scalapack.cpp", "cosma_pxgemm.cpp")], ["cosma", "cosma_b200", "cosma_blacs_lite"]),
+    ("libcosma_pxgemm_cpp.so", [os.path.join("api", f) for f in ("scalapack.cpp", "cosma_pxgemm.cpp", "costa_pxtransform.cpp")],
+     ["cosma", "cosma_b200", "cosma_blacs_lite"]),
+    ("libcosta_scalapack.so", [os.path.join("api", "costa_scalapack.cpp")], ["cosma_pxgemm_cpp", "cosma"]),
+    ("libcosta_prefixed_scalapack.so", [os.path.join("api", "costa_prefixed_scalapack.cpp")], ["cosma_pxgemm_cpp", "cosma"]),
     ("libcosma_pxgemm.so", [os.path.join("api", "pxgemm.cpp")], ["cosma_pxgemm_cpp", "cosma"]),
     ("libcosma_prefixed_pxgemm.so", [os.path.join("api", "prefixed_pxgemm.cpp")], ["cosma_pxgemm_cpp", "cosma"]),
 ]

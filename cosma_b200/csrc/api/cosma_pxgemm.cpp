@@ -12,7 +12,9 @@ namespace {
 std::mutex g_mu;
 std::map<int, void*> g_grids;  // BLACS grid context -> cosma_b200 grid handle
 
-void* grid_for_context(int ctxt) {
+}  // namespace
+
+void* b200::grid_for_blacs_context(int ctxt) {
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_grids.find(ctxt);
     if (it != g_grids.end()) return it->second;
@@ -27,7 +29,6 @@ void* grid_for_context(int ctxt) {
     g_grids[ctxt] = grid;
     return grid;
 }
-}  // namespace
 
 void pxgemm_release_grids() {
     std::lock_guard<std::mutex> lock(g_mu);
@@ -40,7 +41,7 @@ void pxgemm(const char trans_a, const char trans_b, const int m, const int n, co
             const int* desca, const T* b, const int ib, const int jb, const int* descb, const T beta, T* c, const int ic, const int jc,
             const int* descc) {
     if (m == 0 || n == 0) return;
-    void* grid = grid_for_context(scalapack::get_grid_context(desca, descb, descc));
+    void* grid = b200::grid_for_blacs_context(scalapack::get_grid_context(desca, descb, descc));
     double a2[2], b2[2];
     b200::to_pair(alpha, a2);
     b200::to_pair(beta, b2);

@@ -17,4 +17,10 @@ void pxgemm(const char trans_a, const char trans_b, const int m, const int n, co
 
 // releases the grid handles cached per BLACS context (call before Cblacs_gridexit / MPI_Finalize)
 void pxgemm_release_grids();
+
+namespace b200 {
+// the cosma_b200 process-grid handle of a BLACS grid context (shape, numbering and communicator asked from BLACS as in
+// cosma_pxgemm.cpp:57-69), created on first use and cached; shared by cosma::pxgemm and costa::pxgemr2d / pxtran_op
+void* grid_for_blacs_context(int ctxt);
+}  // namespace b200
 }  // namespace cosma

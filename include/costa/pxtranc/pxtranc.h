@@ -1,0 +1,15 @@
+// p{c,z}tranc: conjugate transpose of a complex matrix (reference libs/COSTA/src/costa/pxtranc/pxtranc.h:7-20): all-pointer Fortran ABI in lower / upper case, with and without
+// the trailing underscore; sub(C) (m x n) = beta * sub(C) + alpha * op(sub(A)) with sub(A) n x m.
+#pragma once
+#ifdef __cplusplus
+extern "C" {
+#endif
+#define COSTA_B200_TRAN_ABI(NAME, T)                                                                                    \
+    void NAME(const int* m, const int* n, const T* alpha, const T* a, const int* ia, const int* ja, const int* desca,      \
+              const T* beta, T* c, const int* ic, const int* jc, const int* descc)
+COSTA_B200_TRAN_ABI(pctranc, float); COSTA_B200_TRAN_ABI(pctranc_, float); COSTA_B200_TRAN_ABI(PCTRANC, float); COSTA_B200_TRAN_ABI(PCTRANC_, float);
+COSTA_B200_TRAN_ABI(pztranc, double); COSTA_B200_TRAN_ABI(pztranc_, double); COSTA_B200_TRAN_ABI(PZTRANC, double); COSTA_B200_TRAN_ABI(PZTRANC_, double);
+#undef COSTA_B200_TRAN_ABI
+#ifdef __cplusplus
+}
+#endif

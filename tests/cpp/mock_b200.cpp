@@ -513,4 +513,53 @@ int cosma_b200_pzgemm(void* grid, char ta, char tb, int m, int n, int k, const d
     return mock_pgemm(grid, 'z', ta, tb, m, n, k, alpha, a, ia, ja, da, b, ib, jb, db, beta, c, ic, jc, dc);
 }
 
+// p?tran / p?tranu / p?tranc and p?gemr2d: one dense relayout between two block-cyclic sub-matrices
+int cosma_b200_pxtran(void* grid, char dtype, char op, int m, int n, const double* alpha, const void* a, int ia, int ja, const int* da, const double* beta,
+                      void* c, int ic, int jc, const int* dc, void*) {
+    try {
+        MockGrid& g = *static_cast<MockGrid*>(grid);
+        if (m == 0 || n == 0) return COSMA_B200_OK;
+        const int eb = elem_bytes(dtype), rank = g.comm->rank;
+        const bool in_grid = rank < g.nprow * g.npcol;
+        costa::erased_layout LA = costa::erased_scalapack_layout(da[8], da[2], da[3], ia, ja, n, m, da[4], da[5], g.nprow, g.npcol, g.order, da[6], da[7],
+                                                                 const_cast<void*>(a), eb, 'C', in_grid ? rank : -1);
+        costa::erased_layout LC = costa::erased_scalapack_layout(dc[8], dc[2], dc[3], ic, jc, m, n, dc[4], dc[5], g.nprow, g.npcol, g.order, dc[6], dc[7], c,
+                                                                 eb, 'C', in_grid ? rank : -1);
+        LA.grid.n_ranks = LC.grid.n_ranks = g.comm->size;
+        const bool cplx = dtype == 'c' || dtype == 'z';
+        const double a2[2] = {alpha[0], cplx ? alpha[1] : 0.0}, b2[2] = {beta[0], cplx ? beta[1] : 0.0};
+        op = static_cast<char>(std::toupper(op));
+        switch (dtype) {
+            case 's': transform_t<float>(*g.comm, LA, LC, op, a2, b2); break;
+            case 'd': transform_t<double>(*g.comm, LA, LC, op, a2, b2); break;
+            case 'c': transform_t<std::complex<float>>(*g.comm, LA, LC, op, a2, b2); break;
+            default: transform_t<std::complex<double>>(*g.comm, LA, LC, op, a2, b2); break;
+        }
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) { return fail(e); }
+}
+int cosma_b200_pxgemr2d(void* grid_a, void* grid_c, char dtype, int m, int n, const void* a, int ia, int ja, const int* da, void* c, int ic, int jc,
+                        const int* dc, void*) {
+    try {
+        MockGrid& ga = *static_cast<MockGrid*>(grid_a);
+        MockGrid& gc = *static_cast<MockGrid*>(grid_c);
+        if (m == 0 || n == 0) return COSMA_B200_OK;
+        if (ga.comm != gc.comm) throw std::runtime_error("mock: p?gemr2d grids on different communicators");
+        const int eb = elem_bytes(dtype), rank = ga.comm->rank;
+        costa::erased_layout LA = costa::erased_scalapack_layout(da[8], da[2], da[3], ia, ja, m, n, da[4], da[5], ga.nprow, ga.npcol, ga.order, da[6], da[7],
+                                                                 const_cast<void*>(a), eb, 'C', rank < ga.nprow * ga.npcol ? rank : -1);
+        costa::erased_layout LC = costa::erased_scalapack_layout(dc[8], dc[2], dc[3], ic, jc, m, n, dc[4], dc[5], gc.nprow, gc.npcol, gc.order, dc[6], dc[7], c,
+                                                                 eb, 'C', rank < gc.nprow * gc.npcol ? rank : -1);
+        LA.grid.n_ranks = LC.grid.n_ranks = ga.comm->size;
+        const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+        switch (dtype) {
+            case 's': transform_t<float>(*ga.comm, LA, LC, 'N', one, zero); break;
+            case 'd': transform_t<double>(*ga.comm, LA, LC, 'N', one, zero); break;
+            case 'c': transform_t<std::complex<float>>(*ga.comm, LA, LC, 'N', one, zero); break;
+            default: transform_t<std::complex<double>>(*ga.comm, LA, LC, 'N', one, zero); break;
+        }
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
 }  // extern "C"

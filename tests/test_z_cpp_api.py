@@ -25,6 +25,7 @@ PROGRAMS = {
     "test_multiply": (os.path.join(CPP, "test_multiply.cpp"), [], True),
     "test_multiply_using_layout": (os.path.join(CPP, "test_multiply_using_layout.cpp"), [], True),
     "test_costa_examples": (os.path.join(CPP, "test_costa_examples.cpp"), [], False),
+    "test_pxtran": (os.path.join(CPP, "test_pxtran.cpp"), ["costa_prefixed_scalapack", "costa_scalapack", "cosma_pxgemm_cpp", "cosma_blacs_lite"], False),
     "test_pxgemm": (os.path.join(CPP, "test_pxgemm.cpp"), ["cosma_prefixed_pxgemm", "cosma_pxgemm", "cosma_pxgemm_cpp", "cosma_blacs_lite"], True),
     "cosma_miniapp": (os.path.join(ROOT, "miniapp", "cosma_miniapp.cpp"), [], False),
     "pxgemm_miniapp": (os.path.join(ROOT, "miniapp", "pxgemm_miniapp.cpp"), ["cosma_pxgemm_cpp", "cosma_blacs_lite"], False),
@@ -86,7 +87,14 @@ def test_host_libraries_export_the_reference_symbols(host_libs):
             assert " T %s\n" % name in px, name
         for name in ("cosma_p%sgemm" % t, "cosma_p%sgemm_" % t, "COSMA_P%sGEMM" % t.upper(), "COSMA_P%sGEMM_" % t.upper()):
             assert " T %s\n" % name in pre, name
+    sc, psc = symbols("libcosta_scalapack.so"), symbols("libcosta_prefixed_scalapack.so")
+    for low in ["p%sgemr2d" % t for t in "sdcz"] + ["pstran", "pdtran", "pctranu", "pztranu", "pctranc", "pztranc"]:
+        for name in (low, low + "_", low.upper(), low.upper() + "_"):
+            assert " T %s\n" % name in sc, name
+        for name in ("costa_" + low, "costa_" + low + "_", "COSTA_" + low.upper(), "COSTA_" + low.upper() + "_"):
+            assert " T %s\n" % name in psc, name
     cpp = symbols("libcosma_pxgemm_cpp.so")
+    assert "void costa::pxgemr2d<double>(int, int, double const*" in cpp and "void costa::pxtran_op<std::complex<float>>(" in cpp
     assert "void cosma::pxgemm<double>(char, char, int, int, int, double, double const*" in cpp
     assert "void cosma::pxgemm<std::complex<double>>(" in cpp
 
@@ -94,7 +102,10 @@ def test_host_libraries_export_the_reference_symbols(host_libs):
 @pytest.mark.parametrize("header", ["cosma/multiply.hpp", "cosma/matrix.hpp", "cosma/context.hpp", "cosma/strategy.hpp", "cosma/mapper.hpp",
                                     "cosma/cinterface.hpp", "cosma/cosma_pxgemm.hpp", "cosma/pxgemm.h", "cosma/prefixed_pxgemm.h",
                                     "costa/layout.hpp", "costa/grid2grid/transform.hpp", "costa/grid2grid/transformer.hpp",
-                                    "costa/grid2grid/scalapack_layout.hpp", "cosma_b200.h"])
+                                    "costa/grid2grid/scalapack_layout.hpp", "costa/grid2grid/comm_volume.hpp", "costa/grid2grid/ranks_reordering.hpp",
+                                    "costa/pxgemr2d/costa_pxgemr2d.hpp", "costa/pxtran_op/costa_pxtran_op.hpp", "costa/pxgemr2d/pxgemr2d.h",
+                                    "costa/pxtran/pxtran.h", "costa/pxtranu/prefixed_pxtranu.h", "costa/pxtranc/pxtranc.h", "cosma/blacs.hpp",
+                                    "cosma/scalapack.hpp", "cosma/process_group.hpp", "cosma_b200.h"])
 def test_public_headers_are_self_contained(header, tmp_path):
     src = tmp_path / "t.cpp"
     src.write_text("#include <%s>\nint main() { return 0; }\n" % header)
@@ -148,7 +159,7 @@ def _run_on_mock(np_, argv, timeout=300):
 
 @pytest.mark.parametrize("name,np_", [("test_multiply", 2), ("test_multiply", 4), ("test_multiply", 7), ("test_multiply", 16),
                                       ("test_multiply_using_layout", 2), ("test_multiply_using_layout", 6), ("test_pxgemm", 2), ("test_pxgemm", 8),
-                                      ("test_costa_examples", 4)])
+                                      ("test_costa_examples", 4), ("test_pxtran", 1), ("test_pxtran", 4), ("test_pxtran", 6)])
 def test_cpp_programs_multirank_on_cpu(host_libs, oracle, name, np_):
     """The C++ test programs on 2..16 RANKS without a GPU: the whole host layer is real (communicators, idle ranks, strategies,
     coordinate maps, layout conversion, BLACS-lite, the MPI-name subset, the programs' own message protocols); only the C ABI entry
@@ -193,7 +204,7 @@ def _skip_unless_ranks(np_):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["test_multiply", "test_multiply_using_layout", "test_pxgemm", "test_costa_examples"])
+@pytest.mark.parametrize("name", ["test_multiply", "test_multiply_using_layout", "test_pxgemm", "test_costa_examples", "test_pxtran"])
 @pytest.mark.parametrize("np_", [1, 2, 4, 8])
 def test_cpp_program(host_libs, oracle, name, np_):
     _skip_unless_ranks(np_)
