@@ -107,6 +107,20 @@ class grid_layout {
 
     void reorder_ranks(std::vector<int>& reordering) { grid.reorder_ranks(reordering); }
 
+    // view the same memory as the transposed matrix (reference grid_layout::transpose, grid_layout.hpp:27-30): grid lines and
+    // block coordinates swap, and a column-major block read as its transpose is a row-major block with the same stride
+    void transpose() {
+        grid = grid.transposed();
+        ordering = ordering == 'C' ? 'R' : 'C';
+        for (std::size_t i = 0; i < blocks.num_blocks(); ++i) {
+            auto& b = blocks.get_block(i);
+            std::swap(b.rows_interval, b.cols_interval);
+            std::swap(b.coordinates.first, b.coordinates.second);
+            b.transposed = !b.transposed;
+            b.set_ordering(ordering);
+        }
+    }
+
     // host-side element-wise helpers (host-resident blocks only)
     void scale_by(const T beta) {
         for (std::size_t i = 0; i < blocks.num_blocks(); ++i) blocks.get_block(i).scale_by(beta);

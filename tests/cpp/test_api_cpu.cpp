@@ -58,6 +58,12 @@ int main(int argc, char** argv) {
         L.initialize([](int i, int j) { return 100.0 * i + j; });
         CHECK_TRUE(local[0] == 0.0 && local[3] == 300.0 && local[4] == 800.0 && local[6] == 1.0 && local[3 * 6 + 5] == 906.0);
         CHECK_TRUE(L.validate([](int i, int j) { return 100.0 * i + j; }, 0.0));
+        // the transposed view of the same memory: element (i, j) is the old (j, i)
+        L.transpose();
+        CHECK_TRUE(L.num_rows() == 7 && L.num_cols() == 10 && L.ordering == 'R' && L.grid.owner(1, 0) == 1 && L.grid.owner(0, 1) == 2);
+        CHECK_TRUE(L.validate([](int i, int j) { return 100.0 * j + i; }, 0.0));
+        L.transpose();
+        CHECK_TRUE(L.ordering == 'C' && L.validate([](int i, int j) { return 100.0 * i + j; }, 0.0));
     }
     // no GPU on this box: compute entry points must fail loudly, never fall back
     {
