@@ -1,6 +1,7 @@
 // extern "C" access to the host planning layer (Strategy, Mapper): used by the Python mirror, the tests (which pin
 // these against the unmodified reference in oracle/_ref) and by foreign-language hosts.
 #include "../../../include/cosma_b200.h"
+#include <cosma/adapt_strategy.hpp>
 #include <cosma/mapper.hpp>
 #include <cosma/strategy.hpp>
 #include <costa/grid2grid/comm_volume.hpp>
@@ -128,6 +129,28 @@ int cosma_b200_optimal_reordering(int n_ranks, const long long* volume, int* per
         const std::vector<int> perm = costa::optimal_reordering(vol, n_ranks, re);
         for (int i = 0; i < n_ranks; ++i) permutation[i] = perm[i];
         if (reordered) *reordered = re ? 1 : 0;
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        cosma_b200::set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+// cosma::adapt_strategy_to_block_cyclic_grid for the three 9-int descriptors of a p?gemm call; the prefix ("" = none) is written
+// to out. Feed it to cosma_b200_strategy as `prefix` to obtain the completed strategy.
+int cosma_b200_adapt_strategy(int m, int n, int k, int P, const int* desca, int ia, int ja, const int* descb, int ib, int jb, const int* descc, int ic,
+                              int jc, char transa, char transb, int nprow, int npcol, char order, char* out, int out_len) {
+    try {
+        if (!desca || !descb || !descc || !out) return COSMA_B200_INVALID_ARG;
+        auto of = [](const int* d, int i, int j) {
+            cosma::block_cyclic_desc b;
+            b.rows = d[2]; b.cols = d[3]; b.block_rows = d[4]; b.block_cols = d[5]; b.i = i; b.j = j;
+            return b;
+        };
+        const std::string s = cosma::adapt_strategy_to_block_cyclic_grid(m, n, k, P, of(desca, ia, ja), of(descb, ib, jb), of(descc, ic, jc), transa, transb,
+                                                                         nprow, npcol, order);
+        if (static_cast<int>(s.size()) + 1 > out_len) return COSMA_B200_INVALID_ARG;
+        std::strcpy(out, s.c_str());
         return COSMA_B200_OK;
     } catch (const std::exception& e) {
         cosma_b200::set_last_error(e.what());

@@ -11,6 +11,7 @@
 // its context, context.cpp:80-125, and re-derives the COSTA messages on every call).
 #include "exec_internal.h"
 
+#include <cosma/adapt_strategy.hpp>
 #include <cosma/environment_variables.hpp>
 #include <costa/erased_layout.hpp>
 #include <costa/grid2grid/comm_volume.hpp>
@@ -264,7 +265,8 @@ int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, 
     // that as much of A, B and C as possible is already where COSMA's layout wants it; every rank derives the same
     // permutation from the global grids
     std::vector<int> perm;
-    if (c->size > 1 && c->comm && relabelling_enabled()) {
+    const bool adapted = steps && *steps;  // a strategy adapted to the caller's grid is not relabelled (cosma_pxgemm.cpp:255-283)
+    if (c->size > 1 && c->comm && relabelling_enabled() && !adapted) {
         const NativeGrids& ng = native_grids(c->size, m, n, k, steps);
         costa::comm_volume vol = costa::communication_volume(A.grid, ng.g[0], ta);
         vol += costa::communication_volume(B.grid, ng.g[1], tb);
@@ -503,7 +505,20 @@ static int xpgemm(void* grid, char dtype, char transa, char transb, int m, int n
             costa::erased_layout LA = layout_of(0, ia, ja, a_subm, a_subn), LB = layout_of(1, ib, jb, b_subm, b_subn),
                                LC = layout_of(2, ic, jc, m, n);
             LA.grid.n_ranks = LB.grid.n_ranks = LC.grid.n_ranks = g->comm->size;
-            rc = layout_multiply(g->comm, dtype, ta, tb, m, n, k, a2, b2, LA, LB, LC, "", stream, nullptr);
+            // COSMA_ADAPT_STRATEGY=ON (the reference's default; opt-in here): start the strategy with the steps that
+            // reproduce the block-cyclic grid of the largest operand, so that this operand needs (almost) no relayout
+            std::string steps;
+            if (g->comm->size > 1 && cosma::env_var_defined("COSMA_ADAPT_STRATEGY") && cosma::get_adapt_strategy()) {
+                auto of = [](const int* d, int i, int j) {
+                    cosma::block_cyclic_desc b;
+                    b.rows = d[2]; b.cols = d[3]; b.block_rows = d[4]; b.block_cols = d[5]; b.i = i; b.j = j;
+                    return b;
+                };
+                const std::string prefix = cosma::adapt_strategy_to_block_cyclic_grid(m, n, k, g->comm->size, of(desca, ia, ja), of(descb, ib, jb),
+                                                                                      of(descc, ic, jc), ta, tb, g->nprow, g->npcol, g->order);
+                if (!prefix.empty()) steps = cosma::parse_strategy(m, n, k, static_cast<size_t>(g->comm->size), prefix).to_string();
+            }
+            rc = layout_multiply(g->comm, dtype, ta, tb, m, n, k, a2, b2, LA, LB, LC, steps.c_str(), stream, nullptr);
         }
         if (rc != COSMA_B200_OK) return rc;
         if (staged[2])

@@ -198,6 +198,11 @@ COSMA_B200_API int cosma_b200_comm_volume(int rowblocks_a, int colblocks_a, cons
                                           int rowblocks_b, int colblocks_b, const int* rowsplit_b, const int* colsplit_b, const int* owners_b,
                                           char trans, int n_ranks, long long* volume);
 COSMA_B200_API int cosma_b200_optimal_reordering(int n_ranks, const long long* volume, int* permutation, int* reordered);
+/* cosma::adapt_strategy_to_block_cyclic_grid (src/cosma/cosma_pxgemm.cpp:517-650): the strategy prefix that reproduces the
+ * block-cyclic grid of the largest operand of a p?gemm call ("" when the reference's conditions do not hold). */
+COSMA_B200_API int cosma_b200_adapt_strategy(int m, int n, int k, int P, const int* desca, int ia, int ja, const int* descb, int ib, int jb,
+                                             const int* descc, int ic, int jc, char transa, char transb, int nprow, int npcol, char order,
+                                             char* out, int out_len);
 /* ScaLAPACK NUMROC. */
 COSMA_B200_API int cosma_b200_numroc(int n, int nb, int iproc, int isrcproc, int nprocs);
 

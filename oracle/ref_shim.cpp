@@ -304,3 +304,29 @@ extern "C" int ref_optimal_reordering(int n_ranks, const long long* volume, int*
         return -1;
     }
 }
+
+// ---- cosma::adapt_strategy_to_block_cyclic_grid of the unmodified reference (cosma_pxgemm.cpp:517-650) ---------------------------
+#include <cosma/cosma_pxgemm.hpp>
+extern "C" int ref_adapt_strategy(int m, int n, int k, int P, const int* desca, int ia, int ja, const int* descb, int ib, int jb, const int* descc, int ic,
+                                  int jc, char transa, char transb, int nprow, int npcol, char order, char* out, int out_len) {
+    try {
+        std::vector<int> divisors;
+        std::string dims, types;
+        cosma::scalapack::global_matrix_size ma(desca), mb(descb), mc(descc);
+        cosma::scalapack::block_size ba(desca), bb(descb), bc(descc);
+        cosma::adapt_strategy_to_block_cyclic_grid(divisors, dims, types, m, n, k, P, ma, mb, mc, ba, bb, bc, ia, ja, ib, jb, ic, jc, transa, transb, nprow,
+                                                   npcol, order);
+        std::string s;
+        for (size_t i = 0; i < divisors.size(); ++i) {
+            if (i) s += ',';
+            s += types[i];
+            s += dims[i];
+            s += std::to_string(divisors[i]);
+        }
+        if ((int)s.size() + 1 > out_len) return -2;
+        std::strcpy(out, s.c_str());
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
