@@ -49,7 +49,7 @@ def _native_layouts(plans, label, arenas, x, shape, P):
     return layouts
 
 
-def run_pdgemm_on_cpu(oracle, c, seed):
+def run_pdgemm_on_cpu(oracle, c, seed, steps="", stats=None):
     nprow, npcol, order, P = c["p_rows"], c["p_cols"], c["order"], c["p_rows"] * c["p_cols"]
     m, n, k, ta, tb, alpha, beta = c["m"], c["n"], c["k"], c["ta"], c["tb"], c["alpha"], c["beta"]
     subs = ((c["ia"], c["ja"]), (c["ib"], c["jb"]), (c["ic"], c["jc"]))
@@ -76,7 +76,7 @@ def run_pdgemm_on_cpu(oracle, c, seed):
                                        nprow, npcol, order, srcs[x][0], srcs[x][1], locs[x][r].ctypes.data, bc[x].local_shape(r)[0], "C", r, 8)
              for r in range(P)] for x in range(3)]
     # phase 0: the multiply plans (automatic strategy, as p?gemm uses) and their arenas
-    plans = [MultiplyPlan(None, m, n, k, "", "d", rank=r, nranks=P, allocate=False) for r in range(P)]
+    plans = [MultiplyPlan(None, m, n, k, steps, "d", rank=r, nranks=P, allocate=False) for r in range(P)]
     arenas = [[np.zeros(max(pl.arena_elements[x], 1), dtype=np.float64) for x in range(3)] for pl in plans]
     native = [_native_layouts(plans, "ABC"[x], arenas, x, ((m, k), (k, n), (m, n))[x], P) for x in range(3)]
     # phase 1: relayout op(sub(A)), op(sub(B)) into the native layout -- one exchange, two transforms
@@ -84,6 +84,11 @@ def run_pdgemm_on_cpu(oracle, c, seed):
     for r in range(P):
         tp = costa.TransformPlan(None, "d", [(user[0][r], native[0][r], ta, 1.0, 0.0), (user[1][r], native[1][r], tb, 1.0, 0.0)], rank=r, nranks=P)
         tin.append(tp.export()); tp.destroy()
+        if stats is not None:  # how much of A alone would leave this rank
+            ta_only = costa.TransformPlan(None, "d", [(user[0][r], native[0][r], ta, 1.0, 0.0)], rank=r, nranks=P)
+            stats["a_remote"] = stats.get("a_remote", 0) + ta_only.stats()["remote_elements"]
+            stats["a_local"] = stats.get("a_local", 0) + ta_only.stats()["local_elements"]
+            ta_only.destroy()
     sim.simulate(oracle, "d", tin, [(1.0, 0.0), (1.0, 0.0)])
     # phase 2: the compiled schedule, alpha = 1, beta = 0
     schedule_sim.run_schedules(plans, arenas, 1.0, 0.0)
@@ -121,3 +126,19 @@ def test_most_parameter_sets_have_a_product():
     cases = _cases()
     assert len(cases) == 50
     assert sum(1 for c in cases if c["m"] and c["n"] and c["k"] and c["alpha"] != 0) >= 40
+
+
+@pytest.mark.parametrize("order,prefix", [("R", "sm4,sk6,pm2,pk2"), ("C", "sm4,sk6,pk2,pm2")])
+def test_adapted_strategy_leaves_the_largest_operand_in_place(lib, oracle, order, prefix):
+    """COSMA_ADAPT_STRATEGY in miniature (the size threshold of the reference, 1e7 elements per rank, is out of reach of a numpy
+    simulation, so the prefix is written out by the same rule: sequential steps over the block-cycle repetitions, then the process
+    grid): with the adapted strategy COSMA's native layout of A IS the caller's block-cyclic layout -- its relayout moves nothing
+    between ranks -- and the product is still exact; with the automatic strategy most of A travels."""
+    c = dict(ma=64, na=96, mb=96, nb=32, mc=64, nc=32, bma=8, bna=8, bmb=8, bnb=8, bmc=8, bnc=8, ia=1, ja=1, ib=1, jb=1, ic=1, jc=1, m=64, n=32, k=96,
+             ta="N", tb="N", alpha=1.0, beta=1.0, p_rows=2, p_cols=2, order=order, src_ma=0, src_na=0, src_mb=0, src_nb=0, src_mc=0, src_nc=0)
+    adapted, automatic = {}, {}
+    got, want, strategy = run_pdgemm_on_cpu(oracle, c, 7, steps=prefix, stats=adapted)
+    assert strategy.startswith(prefix) and np.array_equal(got, want)
+    assert adapted["a_remote"] == 0 and adapted["a_local"] == 64 * 96
+    got, want, strategy = run_pdgemm_on_cpu(oracle, c, 7, stats=automatic)
+    assert np.array_equal(got, want) and automatic["a_remote"] > 0
