@@ -49,7 +49,7 @@ def sources():
 # The C++ host layer (the reference's public API: cosma::multiply, CosmaMatrix, costa::transform, the C interface, p?gemm).
 # Plain g++, no CUDA headers: it reaches the GPU only through include/cosma_b200.h. Library split as in the reference
 # (src/cosma/CMakeLists.txt:30-110): cosma | cosma_pxgemm_cpp | cosma_pxgemm (ScaLAPACK names) | cosma_prefixed_pxgemm.
-HOST_PLANNING = ["strategy.cpp", "mapper.cpp", "interval.cpp", "math_utils.cpp", "environment_variables.cpp", "costa_layout.cpp", "costa_reorder.cpp", "adapt_strategy.cpp"]
+HOST_PLANNING = ["strategy.cpp", "mapper.cpp", "interval.cpp", "math_utils.cpp", "environment_variables.cpp", "costa_layout.cpp", "costa_reorder.cpp", "adapt_strategy.cpp", "auto_strategy.cpp", "schedule.cpp"]
 HOST_LIBS = [
     ("libcosma.so", [os.path.join("host", f) for f in HOST_PLANNING] +
      [os.path.join("api", f) for f in ("process_group.cpp", "runtime.cpp", "context.cpp", "matrix.cpp", "multiply.cpp", "costa_api.cpp",

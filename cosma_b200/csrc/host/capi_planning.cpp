@@ -2,6 +2,7 @@
 // these against the unmodified reference in oracle/_ref) and by foreign-language hosts.
 #include "../../../include/cosma_b200.h"
 #include <cosma/adapt_strategy.hpp>
+#include <cosma/auto_strategy.hpp>
 #include <cosma/mapper.hpp>
 #include <cosma/strategy.hpp>
 #include <costa/grid2grid/comm_volume.hpp>
@@ -151,6 +152,25 @@ int cosma_b200_adapt_strategy(int m, int n, int k, int P, const int* desca, int 
                                                                          nprow, npcol, order);
         if (static_cast<int>(s.size()) + 1 > out_len) return COSMA_B200_INVALID_ARG;
         std::strcpy(out, s.c_str());
+        return COSMA_B200_OK;
+    } catch (const std::exception& e) {
+        cosma_b200::set_last_error(e.what());
+        return COSMA_B200_INVALID_ARG;
+    }
+}
+
+// cosma::fit_strategy_to_memory (auto_strategy.hpp): the strategy whose COMPILED schedule needs at most budget_bytes of device
+// memory per rank for elements of elem_bytes; *footprint_bytes = what it needs. INVALID_ARG (with last_error) when nothing fits.
+int cosma_b200_fit_strategy(int m, int n, int k, int P, const char* prefix, int elem_bytes, long long budget_bytes, char* out, int out_len,
+                            int* P_out, long long* footprint_bytes) {
+    try {
+        if (!out || elem_bytes < 1) return COSMA_B200_INVALID_ARG;
+        const cosma::Strategy st = cosma::fit_strategy_to_memory(m, n, k, static_cast<size_t>(P), prefix ? prefix : "", budget_bytes / elem_bytes);
+        const std::string s = st.to_string();
+        if (static_cast<int>(s.size()) + 1 > out_len) return COSMA_B200_INVALID_ARG;
+        std::strcpy(out, s.c_str());
+        if (P_out) *P_out = static_cast<int>(st.P);
+        if (footprint_bytes) *footprint_bytes = cosma::schedule_footprint_elements(st) * elem_bytes;
         return COSMA_B200_OK;
     } catch (const std::exception& e) {
         cosma_b200::set_last_error(e.what());

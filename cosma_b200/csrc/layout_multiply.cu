@@ -12,6 +12,7 @@
 #include "exec_internal.h"
 
 #include <cosma/adapt_strategy.hpp>
+#include <cosma/auto_strategy.hpp>
 #include <cosma/environment_variables.hpp>
 #include <costa/erased_layout.hpp>
 #include <costa/grid2grid/comm_volume.hpp>
@@ -154,15 +155,15 @@ int scale_layout(char dtype, const costa::erased_layout& C, const double* beta, 
 struct NativeGrids {
     costa::assigned_grid2D g[3];
 };
-const NativeGrids& native_grids(int nranks, int m, int n, int k, const char* steps) {
+const NativeGrids& native_grids(int nranks, int m, int n, int k, const char* steps, char dtype) {
     static std::mutex mu;
     static std::map<std::string, NativeGrids> cache;
-    const std::string key = std::to_string(nranks) + ":" + std::to_string(m) + ":" + std::to_string(n) + ":" + std::to_string(k) + ":" + (steps ? steps : "");
+    const std::string key = std::string(1, dtype) + std::to_string(nranks) + ":" + std::to_string(m) + ":" + std::to_string(n) + ":" + std::to_string(k) + ":" + (steps ? steps : "");
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     NativeGrids ng;
-    const cosma::Strategy strategy = cosma::parse_strategy(m, n, k, static_cast<size_t>(nranks), steps ? steps : "");
+    const cosma::Strategy strategy = cosma::automatic_strategy(m, n, k, static_cast<size_t>(nranks), steps ? steps : "", dtype_bytes(dtype));  // as the plan
     for (int x = 0; x < 3; ++x) {
         const cosma::Mapper mapper("ABC"[x], strategy, 0);
         ng.g[x].grid.rows_split = mapper.row_split();
@@ -267,7 +268,7 @@ int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, 
     std::vector<int> perm;
     const bool adapted = steps && *steps;  // a strategy adapted to the caller's grid is not relabelled (cosma_pxgemm.cpp:255-283)
     if (c->size > 1 && c->comm && relabelling_enabled() && !adapted) {
-        const NativeGrids& ng = native_grids(c->size, m, n, k, steps);
+        const NativeGrids& ng = native_grids(c->size, m, n, k, steps, dtype);
         costa::comm_volume vol = costa::communication_volume(A.grid, ng.g[0], ta);
         vol += costa::communication_volume(B.grid, ng.g[1], tb);
         vol += costa::communication_volume(ng.g[2], C.grid, 'N');

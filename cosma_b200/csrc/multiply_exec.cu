@@ -4,6 +4,8 @@
 // gpu/nccl_utils.cpp:45-280, which stage through host memory around every collective); local compute = the sm_100a
 // DGEMM/ZGEMM kernels. Operands never leave HBM.
 #include "exec_internal.h"
+
+#include <cosma/auto_strategy.hpp>
 #include "gemm_f64_sm100.h"
 #include "gemm_tf32x3_sm100.h"
 #include "host_stream.h"
@@ -265,7 +267,8 @@ static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int 
         }
         cosma::Strategy strategy;
         if (P == 0) {
-            strategy = cosma::parse_strategy(m, n, k, nranks, steps ? steps : "");
+            // automatic / prefixed strategy: COSMA_CPU_MAX_MEMORY and COSMA_B200_DEVICE_MEMORY_MB apply (auto_strategy.hpp)
+            strategy = cosma::automatic_strategy(m, n, k, nranks, steps ? steps : "", (dtype == 'd' || dtype == 'z' ? 8 : 4) * (dtype == 'z' || dtype == 'c' ? 2 : 1));
         } else {
             const std::string st = steps ? steps : "";
             if (st.find_first_not_of(" ,") == std::string::npos) {

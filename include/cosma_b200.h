@@ -203,6 +203,12 @@ COSMA_B200_API int cosma_b200_optimal_reordering(int n_ranks, const long long* v
 COSMA_B200_API int cosma_b200_adapt_strategy(int m, int n, int k, int P, const int* desca, int ia, int ja, const int* descb, int ib, int jb,
                                              const int* descc, int ic, int jc, char transa, char transb, int nprow, int npcol, char order,
                                              char* out, int out_len);
+/* The automatic strategy tightened with sequential steps until the device arenas of its COMPILED schedule (local matrices +
+ * communication workspace) fit budget_bytes per rank. The same is applied inside cosma_b200_plan_create (steps = ""),
+ * ?multiply_using_layout and p?gemm when COSMA_B200_DEVICE_MEMORY_MB is set; COSMA_CPU_MAX_MEMORY [MB] keeps its reference meaning
+ * (limit of the Strategy's own memory model). */
+COSMA_B200_API int cosma_b200_fit_strategy(int m, int n, int k, int P, const char* prefix, int elem_bytes, long long budget_bytes, char* out,
+                                           int out_len, int* P_out, long long* footprint_bytes);
 /* ScaLAPACK NUMROC. */
 COSMA_B200_API int cosma_b200_numroc(int n, int nb, int iproc, int isrcproc, int nprocs);
 
