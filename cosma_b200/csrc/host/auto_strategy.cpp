@@ -31,6 +31,7 @@ Strategy fit_strategy_to_memory(int m, int n, int k, size_t P, const std::string
     if (schedule_footprint_elements(s) <= budget_elements) return s;
     // tighten the Strategy's own limit (its model counts the reference's buffers, ours are leaner) until the real arenas fit
     long long limit = s.memory_used > 0 ? s.memory_used : std::numeric_limits<long long>::max() / 4;
+    const Strategy::quiet_errors hush;  // infeasible limits are part of the search, not news
     for (int it = 0; it < 600; ++it) {
         limit = limit - std::max<long long>(limit / 48, 1);  // fine steps: every limit may select a different splitting
         if (limit <= 0) break;

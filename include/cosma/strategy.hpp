@@ -52,6 +52,11 @@ class Strategy {
     void square_strategy(bool& incomplete_strategy);
     bool add_step(long long& prev_m, long long& prev_n, long long& prev_k, int& prev_P, char step, char dim_label, int divisor);
     void throw_exception(const std::string& message);
+    // while one of these lives on the calling thread, throw_exception does not print (used by searches over memory limits)
+    struct quiet_errors {
+        quiet_errors();
+        ~quiet_errors();
+    };
 
     bool split_m(size_t i) const { return split_dimension[i] == 'm'; }
     bool split_n(size_t i) const { return split_dimension[i] == 'n'; }
