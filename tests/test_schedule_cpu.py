@@ -59,3 +59,16 @@ def test_arena_is_bounded(lib):
     kinds = [(op["kind"], op.get("matrix"), op.get("ring")) for op in pl.ops()]
     assert kinds == [("allgather", 1, [3, 7]), ("allgather", 0, [1, 3]), ("gemm", None, None), ("reduce", 2, [2, 3])]
     pl.destroy()
+
+
+def test_statistics_tool(lib, capsys):
+    """cosma_b200.statistics (the reference's miniapp/cosma_statistics.cpp in spirit): BASELINE configs[2] at 8 ranks -- two allgathers of
+    2.1 GB, one 16384^3 GEMM, one reduce-scatter; per rank 3/2 x 2.1 GB on the wire and 10.7 GB of arenas."""
+    from cosma_b200 import statistics
+    d = statistics.describe(32768, 32768, 32768, 8)
+    assert d["strategy"] == "pm2,pn2,pk2" and d["P_used"] == 8 and len(d["lines"]) == 4
+    assert d["wire_bytes"] == 3 * 16384 * 8192 * 8 and abs(d["flops"] - 2.0 * 16384 ** 3) < 1
+    assert d["arena_bytes"] == (3 * 16384 * 8192 + 3 * 16384 * 16384 - 0) * 8 or d["arena_bytes"] > 9e9
+    assert statistics.main(["-m", "8192", "-n", "8192", "-k", "1048576", "-P", "8"]) == 0
+    out = capsys.readouterr().out
+    assert "strategy  : pk8" in out and "reduce     C  ring of 8" in out
