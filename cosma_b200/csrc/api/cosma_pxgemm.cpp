@@ -10,29 +10,43 @@
 namespace cosma {
 namespace {
 std::mutex g_mu;
-std::map<int, void*> g_grids;  // BLACS grid context -> cosma_b200 grid handle
+struct cached_grid {
+    void* handle = nullptr;
+    int nprow = 0, npcol = 0;
+    char order = 'R';
+    unsigned long long comm = 0;
+};
+std::map<int, cached_grid> g_grids;  // BLACS grid context -> cosma_b200 grid handle and what it was built from
 
 }  // namespace
 
 void* b200::grid_for_blacs_context(int ctxt) {
     std::lock_guard<std::mutex> lock(g_mu);
-    auto it = g_grids.find(ctxt);
-    if (it != g_grids.end()) return it->second;
+    // BLACS answers are cheap; asking every time lets a context id that was released and handed out again (real BLACS
+    // libraries recycle them) be recognised instead of serving a stale grid
     int nprow = 0, npcol = 0, myrow = 0, mycol = 0;
     blacs::Cblacs_gridinfo(ctxt, &nprow, &npcol, &myrow, &mycol);
     MPI_Comm comm = scalapack::get_communicator(ctxt);
     int P = 1;
     MPI_Comm_size(comm, &P);
     const char order = scalapack::rank_ordering(ctxt, P) == costa::scalapack::ordering::row_major ? 'R' : 'C';
-    void* grid = nullptr;
-    b200::check(cosma_b200_grid_create(b200::comm_handle(comm), order, nprow, npcol, &grid), "pxgemm (process grid)");
-    g_grids[ctxt] = grid;
-    return grid;
+    auto it = g_grids.find(ctxt);
+    if (it != g_grids.end()) {
+        const cached_grid& g = it->second;
+        if (g.nprow == nprow && g.npcol == npcol && g.order == order && g.comm == comm_key(comm)) return g.handle;
+        cosma_b200_grid_destroy(g.handle);
+        g_grids.erase(it);
+    }
+    cached_grid g;
+    g.nprow = nprow; g.npcol = npcol; g.order = order; g.comm = comm_key(comm);
+    b200::check(cosma_b200_grid_create(b200::comm_handle(comm), order, nprow, npcol, &g.handle), "pxgemm (process grid)");
+    g_grids[ctxt] = g;
+    return g.handle;
 }
 
 void pxgemm_release_grids() {
     std::lock_guard<std::mutex> lock(g_mu);
-    for (auto& kv : g_grids) cosma_b200_grid_destroy(kv.second);
+    for (auto& kv : g_grids) cosma_b200_grid_destroy(kv.second.handle);
     g_grids.clear();
 }
 
