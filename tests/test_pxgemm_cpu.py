@@ -142,3 +142,66 @@ def test_adapted_strategy_leaves_the_largest_operand_in_place(lib, oracle, order
     assert adapted["a_remote"] == 0 and adapted["a_local"] == 64 * 96
     got, want, strategy = run_pdgemm_on_cpu(oracle, c, 7, stats=automatic)
     assert np.array_equal(got, want) and automatic["a_remote"] > 0
+
+
+def _random_layout(rng, rows, cols, P, dtype):
+    rs = sim.random_split(rng, rows, int(rng.integers(1, 5)))
+    cs = sim.random_split(rng, cols, int(rng.integers(1, 5)))
+    owners = rng.integers(0, P, size=(len(rs) - 1, len(cs) - 1))
+    return sim.DistMatrix(rs, cs, owners, P, dtype, "C", pad=int(rng.integers(0, 3)))
+
+
+@pytest.mark.parametrize("P", [3, 4, 6])
+@pytest.mark.parametrize("dtype,ta,tb", [("d", "N", "N"), ("d", "T", "N"), ("z", "C", "N"), ("z", "N", "C"), ("d", "T", "T")])
+def test_multiply_using_layout_in_lock_step(lib, oracle, P, dtype, ta, tb):
+    """cosma::multiply_using_layout (reference multiply.cpp:78-213) END TO END on the CPU with the plans the GPU executes: random block
+    layouts with random owners for A, B and C (padded leading dimensions), op(A), op(B) relayouted into COSMA's native layout, the
+    compiled schedule, the result relayouted into C's layout with (alpha, beta); exact on integer-valued matrices, real and complex."""
+    rng = np.random.default_rng(100 * P + ord(ta) + 3 * ord(tb))
+    npdt = np.float64 if dtype == "d" else np.complex128
+    for trial in range(2):
+        m, n, k = (int(rng.integers(220, 300)), int(rng.integers(210, 280)), int(rng.integers(200, 320)))
+        alpha, beta = ((1.0, 0.0), (2.0, -1.0))[trial]
+        A = sim.random_values(rng, (m, k) if ta == "N" else (k, m), dtype)
+        B = sim.random_values(rng, (k, n) if tb == "N" else (n, k), dtype)
+        C = sim.random_values(rng, (m, n), dtype)
+        dA, dB, dC = (_random_layout(rng, X.shape[0], X.shape[1], P, dtype) for X in (A, B, C))
+        dA.scatter(A); dB.scatter(B)
+        dC.fill_padding(7)
+        dC.scatter(C if beta != 0.0 else np.full_like(C, np.nan))
+        plans = [MultiplyPlan(None, m, n, k, "", dtype, rank=r, nranks=P, allocate=False) for r in range(P)]
+        arenas = [[np.zeros(max(pl.arena_elements[x], 1), dtype=npdt) for x in range(3)] for pl in plans]
+        eb = 8 if dtype == "d" else 16
+        native = []
+        for x, shape in enumerate(((m, k), (k, n), (m, n))):
+            per_rank = [plans[0].local_blocks("ABC"[x], r) for r in range(P)]
+            rs = sorted({b[0] for bl in per_rank for b in bl} | {shape[0]})
+            cs = sorted({b[2] for bl in per_rank for b in bl} | {shape[1]})
+            owners = np.zeros((len(rs) - 1, len(cs) - 1), dtype=np.int32)
+            for r, bl in enumerate(per_rank):
+                for (r0, r1, c0, c1) in bl:
+                    owners[rs.index(r0), cs.index(c0)] = r
+            lays = []
+            for r in range(P):
+                blocks, pos = [], 0
+                for (r0, r1, c0, c1) in per_rank[r]:
+                    nr, nc = r1 - r0 + 1, c1 - c0 + 1
+                    blocks.append((rs.index(r0), cs.index(c0), arenas[r][x].ctypes.data + pos * eb, nr))
+                    pos += nr * nc
+                lays.append(costa.custom_layout(rs, cs, owners, blocks, "C"))
+            native.append(lays)
+        tin = []
+        for r in range(P):
+            tp = costa.TransformPlan(None, dtype, [(dA.layout(r), native[0][r], ta, 1.0, 0.0), (dB.layout(r), native[1][r], tb, 1.0, 0.0)], rank=r, nranks=P)
+            tin.append(tp.export()); tp.destroy()
+        sim.simulate(oracle, dtype, tin, [(1.0, 0.0), (1.0, 0.0)])
+        schedule_sim.run_schedules(plans, arenas, 1.0, 0.0)
+        tout = []
+        for r in range(P):
+            tp = costa.TransformPlan(None, dtype, [(native[2][r], dC.layout(r), "N", alpha, beta)], rank=r, nranks=P)
+            tout.append(tp.export()); tp.destroy()
+        sim.simulate(oracle, dtype, tout, [(alpha, beta)])
+        for pl in plans:
+            pl.destroy()
+        want = alpha * (sim.apply_op(A, ta) @ sim.apply_op(B, tb)) + (beta * C if beta != 0.0 else 0)
+        assert np.array_equal(dC.gather(), want.astype(npdt)), (m, n, k, trial)
