@@ -106,7 +106,7 @@ def build_host(force=False):
     outs = []
     for name, _, libs in HOST_LIBS:
         lib = os.path.join(LIBDIR, name)
-        cmd = [CXX, "-shared", "-o", lib] + objs_of[name] + ["-L", LIBDIR] + ["-l" + l for l in libs] + ["-Wl,-rpath,$ORIGIN", "-lpthread"]
+        cmd = [CXX, "-shared", "-o", lib] + objs_of[name] + ["-L", LIBDIR] + ["-l" + l for l in libs] + ["-Wl,-rpath,$ORIGIN", "-lpthread", "-ldl"]
         subprocess.check_call(cmd)
         outs.append(lib)
     return outs

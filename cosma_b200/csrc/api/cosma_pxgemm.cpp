@@ -3,6 +3,9 @@
 // COSMA's layout, the multiply, the relayout into sub(C) with (alpha, beta) -- happens behind cosma_b200_p?gemm.
 #include <cosma/b200_runtime.hpp>
 #include <cosma/cosma_pxgemm.hpp>
+#include <cosma/environment_variables.hpp>
+
+#include <algorithm>
 
 #include <map>
 #include <mutex>
@@ -42,6 +45,11 @@ void* b200::grid_for_blacs_context(int ctxt) {
     b200::check(cosma_b200_grid_create(b200::comm_handle(comm), order, nprow, npcol, &g.handle), "pxgemm (process grid)");
     g_grids[ctxt] = g;
     return g.handle;
+}
+
+bool problem_below_dim_threshold(int m, int n, int k) {
+    static const int threshold = get_cosma_dim_threshold();
+    return std::min(m, std::min(n, k)) < threshold;
 }
 
 void pxgemm_release_grids() {

@@ -15,6 +15,9 @@ void pxgemm(const char trans_a, const char trans_b, const int m, const int n, co
             const int* desca, const T* b, const int ib, const int jb, const int* descb, const T beta, T* c, const int ic, const int jc,
             const int* descc);
 
+// min(m, n, k) < COSMA_DIM_THRESHOLD (reference is_problem_too_small, cosma_pxgemm.cpp:652-655); the threshold defaults to 0
+bool problem_below_dim_threshold(int m, int n, int k);
+
 // releases the grid handles cached per BLACS context (call before Cblacs_gridexit / MPI_Finalize)
 void pxgemm_release_grids();
 

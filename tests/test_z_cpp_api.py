@@ -170,6 +170,20 @@ def test_cpp_programs_multirank_on_cpu(host_libs, oracle, name, np_):
     assert "checks passed (all ranks) = 0," not in out
 
 
+def test_dim_threshold_hands_small_problems_to_the_next_scalapack(host_libs):
+    """COSMA_DIM_THRESHOLD: libcosma_pxgemm.so in front of a (fake) ScaLAPACK; small problems reach the fake, large ones are served."""
+    fake = os.path.join(BIN, "libfake_scalapack.so")
+    os.makedirs(BIN, exist_ok=True)
+    subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", os.path.join(CPP, "fake_scalapack.c"), "-o", fake])
+    exe = os.path.join(BIN, "test_interpose")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(CPP, "test_interpose.cpp"), "-o", exe,
+                           "-L", LIBDIR, "-L", BIN, "-lcosma_pxgemm", "-Wl,--no-as-needed", "-lfake_scalapack", "-Wl,--as-needed", "-lcosma_pxgemm_cpp", "-lcosma_blacs_lite", "-lcosma",
+                           "-lcosma_b200", "-Wl,-rpath," + LIBDIR, "-Wl,-rpath," + BIN])
+    from cosma_b200.launch import launch
+    code, outs = launch(1, [exe], timeout=120, capture=True, env_extra={"LD_PRELOAD": _mock(), "COSMA_DIM_THRESHOLD": "64"})
+    assert code == 0 and "failed = 0" in outs[0], outs[0]
+
+
 @pytest.mark.parametrize("np_,args", [(4, ["-m", "600", "-n", "500", "-k", "700", "-r", "2"]),
                                       (5, ["-m", "300", "-n", "300", "-k", "300", "-r", "1", "-t", "zdouble"]),   # the strategy idles ranks
                                       (6, ["-m", "640", "-n", "640", "-k", "640", "-s", "pm2,pk3", "-r", "1", "-t", "float"])])
