@@ -1,0 +1,34 @@
+"""bench.py's reference arm (the one leg that runs without a GPU): one JSON line with the contract's keys, at N = 1 (the reference's
+cosma::multiply in-process) and at N = 2 (the unmodified reference miniapp on 2 minimpi ranks)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+        "config", "cpu_baseline", "e2e", "gpu_launches"}
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_reference_arm_line(ref, gpus):
+    env = dict(os.environ, RANK="0", WORLD_SIZE=str(gpus))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(gpus), "--steps", "1", "--warmup", "1",
+                          "--mnk", "768,640,512"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert KEYS <= set(d), sorted(KEYS - set(d))
+    assert d["impl"] == "reference" and d["n_gpus"] == gpus and d["unit"] == "TFLOP/s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_other_ranks_of_the_reference_arm_do_nothing(ref):
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ""
