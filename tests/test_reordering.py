@@ -152,3 +152,31 @@ def test_relabelling_finds_cosma_layout_with_reversed_ranks(lib, world):
     perm, flag = _reorder(lib.cosma_b200_optimal_reordering, total)
     assert flag and list(perm) == sigma
     assert _kept_in_place(total, perm) == 3 * m * n
+
+
+def test_baseline_pzgemm_configuration_needs_no_relabelling(lib):
+    """BASELINE configs[4] (16384^2, 256 x 256 blocks on a 2 x 4 row-major grid, A conjugate-transposed) against COSMA's layout for
+    pm2,pn2,pk2: block-cyclic spreads every COSMA block evenly over all ranks, so every pair of ranks exchanges the same volume and the
+    matching keeps the identity."""
+    from cosma_b200 import planning
+    P, m, n, k = 8, 16384, 16384, 16384
+    steps = planning.strategy(m, n, k, P)[0]
+    total = np.zeros((P, P), dtype=np.int64)
+    for label, (rows, cols), tr in (("A", (m, k), "C"), ("B", (k, n), "N"), ("C", (m, n), "N")):
+        per = planning.mapper_layout(label, m, n, k, P, steps)
+        rs = np.array(sorted({b[0] for bl in per for b in bl} | {rows}), dtype=np.int32)
+        cs = np.array(sorted({b[2] for bl in per for b in bl} | {cols}), dtype=np.int32)
+        native = np.zeros((len(rs) - 1, len(cs) - 1), dtype=np.int32)
+        for r, bl in enumerate(per):
+            for (r0, r1, c0, c1) in bl:
+                native[list(rs).index(r0), list(cs).index(c0)] = r
+        ur, uc = (cols, rows) if tr != "N" else (rows, cols)
+        brs, bcs = np.arange(0, ur + 1, 256, dtype=np.int32), np.arange(0, uc + 1, 256, dtype=np.int32)
+        own = np.array([[(i % 2) * 4 + (j % 4) for j in range(len(bcs) - 1)] for i in range(len(brs) - 1)], dtype=np.int32).reshape(-1)
+        u, v = (brs, bcs, own), (rs, cs, np.ascontiguousarray(native.reshape(-1)))
+        total += _volume(lib.cosma_b200_comm_volume, u, v, tr, P) if label != "C" else _volume(lib.cosma_b200_comm_volume, v, u, "N", P)
+    assert int(total.sum()) == 3 * m * n
+    off = total[np.triu_indices(P, 1)]
+    assert (off == off[0]).all() and (np.diag(total) == total[0, 0]).all()
+    perm, flag = _reorder(lib.cosma_b200_optimal_reordering, total)
+    assert not flag and list(perm) == list(range(P))
