@@ -112,6 +112,25 @@ def test_public_headers_are_self_contained(header, tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), str(src)])
 
 
+@pytest.mark.parametrize("source", ["runtime", "context", "matrix", "multiply", "costa_api", "cinterface", "scalapack", "cosma_pxgemm", "costa_pxtransform",
+                                    "pxgemm", "prefixed_pxgemm", "costa_scalapack", "costa_prefixed_scalapack"])
+def test_host_layer_compiles_against_a_real_mpi_header(source):
+    """-DCOSMA_B200_WITH_MPI: MPI_Comm and the MPI calls come from <mpi.h> instead of mpi_compat's process group. No MPI is installed
+    here; the declaration-only mpi.h of the reference checker (oracle/stubs/, MPI_Comm = int) stands in for the header, which is enough
+    to prove that the host layer only uses MPI names a real MPI declares (MPI_Comm_c2f is supplied on the command line)."""
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-DCOSMA_B200_WITH_MPI", "-DMPI_Comm_c2f(c)=(c)", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "cosma_b200", "csrc", "api"), "-I", os.path.join(ROOT, "oracle", "stubs"),
+                           os.path.join(ROOT, "cosma_b200", "csrc", "api", source + ".cpp")])
+
+
+@pytest.mark.parametrize("source", ["tests/cpp/test_multiply.cpp", "tests/cpp/test_multiply_using_layout.cpp", "tests/cpp/test_pxgemm.cpp",
+                                    "tests/cpp/test_pxtran.cpp", "tests/cpp/test_costa_examples.cpp", "miniapp/cosma_miniapp.cpp", "miniapp/pxgemm_miniapp.cpp"])
+def test_programs_compile_against_a_real_mpi_header(source):
+    """The test programs and miniapps only use MPI calls that exist in MPI: they compile unchanged with -DCOSMA_B200_WITH_MPI."""
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-DCOSMA_B200_WITH_MPI", "-DMPI_Comm_c2f(c)=(c)", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, source)])
+
+
 def test_c_abi_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
     src.write_text("#include <cosma_b200.h>\nint main(void) { return cosma_b200_version() == 0; }\n")
