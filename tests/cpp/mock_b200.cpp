@@ -290,6 +290,15 @@ struct MockGrid {
 
 std::uint32_t g_counter = 0;
 
+// the stand-in moves its data over cosma::pg: bring the group up when the library is loaded, on every rank at once (with the
+// MPI-name subset MPI_Init would do it; a build against a real MPI -- tests run that over the reference checker's minimpi -- would
+// otherwise first touch pg on whichever rank calls the C ABI first, and wait for the others forever)
+struct pg_bootstrap {
+    pg_bootstrap() {
+        try { pg::init(); } catch (const std::exception&) {}
+    }
+} g_pg_bootstrap;
+
 }  // namespace
 
 extern "C" {

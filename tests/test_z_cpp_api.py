@@ -131,6 +131,33 @@ def test_programs_compile_against_a_real_mpi_header(source):
                            "-I", os.path.join(ROOT, "oracle", "stubs"), os.path.join(ROOT, source)])
 
 
+def test_host_layer_runs_over_an_mpi_implementation(host_libs, oracle):
+    """The -DCOSMA_B200_WITH_MPI build AT RUN TIME: api/ + host/ + tests/cpp/test_multiply.cpp compiled against the MPI header and linked
+    with the multi-process MPI stand-in that runs the unmodified reference (oracle/stubs/minimpi.cpp, started by oracle/minirun.py),
+    the C ABI underneath replaced by the CPU stand-in. 4 ranks: MPI_Comm_create_group of the active ranks, the ncclUniqueId-style
+    broadcast, idle ranks, all multiply cases that fit 4 ranks."""
+    import socket
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from minirun import launch as mpi_launch
+    api, host = os.path.join(ROOT, "cosma_b200", "csrc", "api"), os.path.join(ROOT, "cosma_b200", "csrc", "host")
+    stubs = os.path.join(ROOT, "oracle", "stubs")
+    exe = os.path.join(BIN, "mpi_test_multiply")
+    srcs = [os.path.join(api, f) for f in ("process_group.cpp", "runtime.cpp", "context.cpp", "matrix.cpp", "multiply.cpp", "costa_api.cpp", "cinterface.cpp")]
+    srcs += [os.path.join(host, f) for f in ("strategy.cpp", "mapper.cpp", "interval.cpp", "math_utils.cpp", "environment_variables.cpp", "costa_layout.cpp",
+                                             "costa_reorder.cpp")]
+    os.makedirs(BIN, exist_ok=True)
+    mock_o = os.path.join(BIN, "mock_b200_nompi.o")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-c", os.path.join(CPP, "mock_b200.cpp"), "-I", os.path.join(ROOT, "include"), "-o", mock_o])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DCOSMA_B200_WITH_MPI", "-DMPI_Comm_c2f(c)=(c)", "-I", os.path.join(ROOT, "include"), "-I", api, "-I", stubs,
+                           os.path.join(CPP, "test_multiply.cpp")] + srcs + [os.path.join(stubs, "minimpi.cpp"), mock_o, "-o", exe,
+                           "-L", os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, COSMA_B200_PG_PORT=str(port), MASTER_ADDR="127.0.0.1")
+    code, outs = mpi_launch(4, ["bash", "-c", "RANK=$MINIMPI_RANK WORLD_SIZE=$MINIMPI_SIZE exec " + exe], env=env, stdout=subprocess.PIPE, timeout=300)
+    text = outs[0].decode()
+    assert code == 0 and "failed = 0" in text and "idle ranks" in text, text[-3000:]
+
+
 def test_c_abi_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
     src.write_text("#include <cosma_b200.h>\nint main(void) { return cosma_b200_version() == 0; }\n")
