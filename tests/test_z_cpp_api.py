@@ -204,7 +204,7 @@ def _run_on_mock(np_, argv, timeout=300):
 
 
 @pytest.mark.parametrize("name,np_", [("test_multiply", 2), ("test_multiply", 4), ("test_multiply", 7), ("test_multiply", 16),
-                                      ("test_multiply_using_layout", 2), ("test_multiply_using_layout", 6), ("test_pxgemm", 2), ("test_pxgemm", 8),
+                                      ("test_multiply_using_layout", 2), ("test_multiply_using_layout", 6), ("test_pxgemm", 2), ("test_pxgemm", 6),
                                       ("test_costa_examples", 4), ("test_pxtran", 1), ("test_pxtran", 4), ("test_pxtran", 6)])
 def test_cpp_programs_multirank_on_cpu(host_libs, oracle, name, np_):
     """The C++ test programs on 2..16 RANKS without a GPU: the whole host layer is real (communicators, idle ranks, strategies,
