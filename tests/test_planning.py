@@ -98,3 +98,40 @@ def test_committed_golden_fixture(planning):
             if label in c["layout"]:
                 lay = planning.mapper_layout(label, m, n, k, c["P_used"], c["steps"])
                 assert [[list(b) for b in blocks] for blocks in lay] == c["layout"][label], (c, label)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_randomised_strategy_and_mapper_parity(lib, ref, seed):
+    """A seeded slice of tools/fuzz_strategy_vs_reference.py / fuzz_mapper_vs_reference.py (4000 + 2400 cases offline, no mismatch):
+    random shapes, rank counts and memory limits; steps, ranks used, memory_used and every rank's block list equal the reference's."""
+    import ctypes
+    import random
+    from cosma_b200 import planning as pl
+    R = ref.ref()
+    rnd = random.Random(seed)
+    checked = 0
+    for _ in range(60):
+        m, n, k = [rnd.choice([rnd.randint(1, 60), rnd.randint(200, 3000), rnd.randint(1000, 40000)]) for _ in range(3)]
+        P = rnd.choice([1, 2, 3, 4, 6, 7, 8, 12, 16, 24, 32])
+        mem = int((m * k + k * n + m * n) // P * rnd.uniform(1.2, 3.0)) + 1 if rnd.random() < 0.3 else 0
+        out = ctypes.create_string_buffer(8192)
+        Po, mu = ctypes.c_int(0), ctypes.c_longlong(0)
+        rc = R.ref_strategy(m, n, k, P, ctypes.c_longlong(mem), b"", out, 8192, ctypes.byref(Po), ctypes.byref(mu))
+        try:
+            steps, P_used, mem_used = pl.strategy(m, n, k, P, mem)
+        except Exception:
+            assert rc < 0
+            continue
+        assert rc >= 0 and (out.value.decode(), Po.value, mu.value) == (steps, P_used, mem_used), (m, n, k, P, mem)
+        for label in "ABC":
+            counts = (ctypes.c_int * max(P_used, 1))()
+            flat = (ctypes.c_int * (4 * 100000))()
+            assert R.ref_mapper_layout(ctypes.c_char(label.encode()), m, n, k, P_used, steps.encode(), counts, flat, 4 * 100000) >= 0
+            ours = pl.mapper_layout(label, m, n, k, P_used, steps)
+            pos, theirs = 0, []
+            for r in range(P_used):
+                theirs.append([tuple(flat[4 * (pos + b):4 * (pos + b) + 4]) for b in range(counts[r])])
+                pos += counts[r]
+            assert ours == theirs, (label, m, n, k, P_used, steps)
+            checked += 1
+    assert checked > 100
