@@ -1,0 +1,91 @@
+"""Randomised distributed parity: random (m, n, k), rank counts and strategies (automatic, memory-limited, or random explicit step
+lists with sequential and parallel steps) run through the UNMODIFIED reference cosma::multiply on P minimpi ranks and through OUR
+compiled schedule in CPU lock-step; every rank's local C must be bit-identical (integer inputs). python tools/fuzz_schedule_vs_reference.py SEED N
+Last run: see DESIGN.md 5a."""
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from cosma_b200 import planning  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from schedule_sim import simulate  # noqa: E402
+from cosma_b200.distributed import MultiplyPlan, gather_local_to_global  # noqa: E402
+
+
+def random_steps(rnd, P):
+    """a random explicit strategy whose parallel divisors multiply to P, with sequential steps sprinkled in"""
+    factors, p, f = [], P, 2
+    while p > 1:
+        while p % f == 0:
+            factors.append(f); p //= f
+        f += 1
+    rnd.shuffle(factors)
+    steps = []
+    for d in factors:
+        if rnd.random() < 0.4:
+            steps.append("s%s%d" % (rnd.choice("mnk"), rnd.choice([2, 3])))
+        steps.append("p%s%d" % (rnd.choice("mnk"), d))
+    if rnd.random() < 0.3:
+        steps.append("s%s%d" % (rnd.choice("mnk"), 2))
+    return ",".join(steps)
+
+
+def main():
+    rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+    N = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    orc.ref()
+    bad = ran = skipped = ref_wrong = 0
+    for it in range(N):
+        P = rnd.choice([1, 2, 3, 4, 6, 8])
+        m, n, k = (rnd.randint(8, 120) for _ in range(3))
+        mode = rnd.random()
+        if mode < 0.5:
+            steps = random_steps(rnd, P)
+        else:
+            steps = ""
+        alpha, beta = rnd.choice([(1.0, 0.0), (1.0, 1.0), (2.0, -1.0)])
+        rng = np.random.default_rng(it)
+        A, B, C = (rng.integers(-4, 6, size=s).astype(np.float64) for s in ((m, k), (k, n), (m, n)))
+        try:
+            planning.strategy(m, n, k, P, 0, steps) if steps else None
+        except Exception:
+            skipped += 1
+            continue
+        try:
+            ref_locals, _ = orc.ref_multiply_ranks("d", m, n, k, P, steps, alpha, beta, A, B, C)
+        except Exception:
+            skipped += 1
+            continue
+        ours = []
+        got, want, _ = simulate(m, n, k, P, steps, alpha=alpha, beta=beta, inputs=(A, B, C), local_c=ours)
+        ours_right = bool(np.array_equal(got, want))
+        same = len(ref_locals) == len(ours)
+        for a, b in zip(ref_locals, ours):
+            same = same and ((a is None) == (b is None)) and (a is None or (a.shape == b.shape and np.array_equal(a, b)))
+        ran += 1
+        if same and ours_right:
+            continue
+        # the reference's own answer, assembled with the (identical) Mapper layout: is IT right?
+        refg = np.zeros((m, n))
+        for r in range(P):
+            pl = MultiplyPlan(None, m, n, k, steps, "d", rank=r, nranks=P, allocate=False)
+            if r < len(ref_locals) and ref_locals[r] is not None and ref_locals[r].size == pl.initial_elements[2]:
+                gather_local_to_global(pl, "C", ref_locals[r], refg)
+            pl.destroy()
+        ref_right = bool(np.array_equal(refg, want))
+        if ours_right and not ref_right:
+            ref_wrong += 1
+            print("REFERENCE WRONG (ours equals the dense product)", m, n, k, P, steps, alpha, beta)
+        else:
+            bad += 1
+            print("MISMATCH", m, n, k, P, steps, alpha, beta, "ours right:", ours_right, "reference right:", ref_right)
+    print("cases run %d, skipped (strategy rejected or reference crashed) %d, reference wrong %d, OUR mismatches %d" % (ran, skipped, ref_wrong, bad))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
