@@ -99,11 +99,11 @@ def test_committed_reference_fixtures(lib, name):
 
 
 def test_randomised_schedules_against_the_live_reference(lib, refd):
-    """A seeded slice of tools/fuzz_schedule_vs_reference.py (254 random problems offline: random shapes, 1-8 ranks, automatic or random
+    """A seeded slice of tools/fuzz_schedule_vs_reference.py (755 random problems offline: random shapes, 1-8 ranks, automatic or random
     explicit strategies mixing sequential and parallel steps, three (alpha, beta) pairs): wherever the reference's answer is right, every
-    rank's local C of our compiled schedule is bit-identical to it; the tool found NO case where ours is wrong, and 5 exotic explicit
-    strategies (a sequential step between two parallel splits of the same dimension, e.g. sm2,pm2,pm2) where the REFERENCE's result
-    differs from the dense product while ours equals it."""
+    rank's local C of our compiled schedule is bit-identical to it; the tool found NO case where ours is wrong, and 21 exotic explicit
+    strategies (e.g. sm2,pm2,pm2 or pk2,sn2,pn2) where the REFERENCE's result differs from the dense product while ours
+    equals it."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
