@@ -27,6 +27,7 @@
 //    exactly 4 real FMA per complex FMA, i.e. no wasted DMMA work.
 #include "sm100_common.cuh"
 #include "gemm_f64_sm100.h"
+#include "repack.h"
 
 #include <cstdio>
 #include <mutex>
@@ -624,6 +625,27 @@ static int gemm_f64_impl(cudaStream_t stream, char transa, char transb, int64_t 
             if (path_used) *path_used = 1;
             return COSMA_B200_OK;
         }
+    }
+    // opt-in: repack what TMA cannot address (odd leading dimension / 8-byte-aligned base) and run the DMMA kernel on the copies
+    if (!aligned && repack_unaligned_enabled() && k >= 64 && m * n >= 128 * 128) {
+        const bool a_bad = (!CPLX && (lda & 1)) || (reinterpret_cast<uintptr_t>(A) & 15);
+        const bool b_bad = (!CPLX && (ldb & 1)) || (reinterpret_cast<uintptr_t>(B) & 15);
+        Repacked ra, rb;
+        const int eb = CPLX ? 16 : 8;
+        cudaError_t e = cudaSuccess;
+        if (a_bad) e = repack_operand(stream, A, lda, ta ? k : m, ta ? m : k, eb, 2, ra);
+        if (e == cudaSuccess && b_bad) e = repack_operand(stream, B, ldb, tb ? n : k, tb ? k : n, eb, 2, rb);
+        if (e == cudaSuccess) {
+            const int st = gemm_f64_impl<CPLX>(stream, transa, transb, m, n, k, alpha, a_bad ? static_cast<const double*>(ra.ptr) : A,
+                                               a_bad ? ra.ld : lda, b_bad ? static_cast<const double*>(rb.ptr) : B, b_bad ? rb.ld : ldb, beta, C,
+                                               ldc, path_used);
+            repack_release(stream, ra);
+            repack_release(stream, rb);
+            return st;
+        }
+        repack_release(stream, ra);
+        repack_release(stream, rb);
+        cudaGetLastError();  // scratch not available: fall through to the generic kernel
     }
     if (!CPLX) {
         dim3 grid(static_cast<unsigned>((m + GT - 1) / GT), static_cast<unsigned>((n + GT - 1) / GT));
