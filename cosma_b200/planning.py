@@ -57,3 +57,27 @@ def global_coordinates(label, m, n, k, P, steps, local_idx, rank):
                                                   ctypes.c_int(rank), ctypes.byref(gi), ctypes.byref(gj))
     _lib.check(st, "cosma_b200_mapper_global_coordinates")
     return gi.value, gj.value
+
+
+def fit_strategy(m, n, k, P, elem_bytes, budget_bytes, prefix=""):
+    """cosma_b200_fit_strategy: the automatic strategy tightened with sequential steps until the arenas of its compiled schedule fit
+    budget_bytes of device memory per rank. -> (steps, ranks used, footprint bytes). Raises when nothing fits."""
+    lib = _lib.load()
+    out = ctypes.create_string_buffer(8192)
+    P_out, foot = ctypes.c_int(0), ctypes.c_longlong(0)
+    st = lib.cosma_b200_fit_strategy(ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(k), ctypes.c_int(P), prefix.encode(), ctypes.c_int(elem_bytes),
+                                     ctypes.c_longlong(budget_bytes), out, ctypes.c_int(8192), ctypes.byref(P_out), ctypes.byref(foot))
+    _lib.check(st, "cosma_b200_fit_strategy")
+    return out.value.decode(), P_out.value, foot.value
+
+
+def adapt_strategy(m, n, k, P, desca, ia, ja, descb, ib, jb, descc, ic, jc, transa, transb, nprow, npcol, order):
+    """cosma_b200_adapt_strategy: the strategy prefix that mirrors the block-cyclic grid of the largest operand ("" if the reference's
+    conditions do not hold). desc*: 9-int ScaLAPACK descriptors (sequences)."""
+    lib = _lib.load()
+    arr = [(ctypes.c_int * 9)(*[int(x) for x in d]) for d in (desca, descb, descc)]
+    out = ctypes.create_string_buffer(512)
+    st = lib.cosma_b200_adapt_strategy(m, n, k, P, arr[0], ia, ja, arr[1], ib, jb, arr[2], ic, jc, ctypes.c_char(transa.encode()),
+                                       ctypes.c_char(transb.encode()), nprow, npcol, ctypes.c_char(order.encode()), out, 512)
+    _lib.check(st, "cosma_b200_adapt_strategy")
+    return out.value.decode()
