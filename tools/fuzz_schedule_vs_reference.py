@@ -49,19 +49,23 @@ def main():
             steps = ""
         alpha, beta = rnd.choice([(1.0, 0.0), (1.0, 1.0), (2.0, -1.0)])
         rng = np.random.default_rng(it)
+        dtype = rnd.choice("ddz")
         A, B, C = (rng.integers(-4, 6, size=s).astype(np.float64) for s in ((m, k), (k, n), (m, n)))
+        if dtype == "z":
+            A, B, C = (x + 1j * rng.integers(-4, 6, size=x.shape) for x in (A, B, C))
+            alpha = alpha * (1 - 0.5j)
         try:
             planning.strategy(m, n, k, P, 0, steps) if steps else None
         except Exception:
             skipped += 1
             continue
         try:
-            ref_locals, _ = orc.ref_multiply_ranks("d", m, n, k, P, steps, alpha, beta, A, B, C)
+            ref_locals, _ = orc.ref_multiply_ranks(dtype, m, n, k, P, steps, alpha, beta, A, B, C)
         except Exception:
             skipped += 1
             continue
         ours = []
-        got, want, _ = simulate(m, n, k, P, steps, alpha=alpha, beta=beta, inputs=(A, B, C), local_c=ours)
+        got, want, _ = simulate(m, n, k, P, steps, alpha=alpha, beta=beta, dtype=dtype, inputs=(A, B, C), local_c=ours)
         ours_right = bool(np.array_equal(got, want))
         same = len(ref_locals) == len(ours)
         for a, b in zip(ref_locals, ours):
@@ -70,19 +74,19 @@ def main():
         if same and ours_right:
             continue
         # the reference's own answer, assembled with the (identical) Mapper layout: is IT right?
-        refg = np.zeros((m, n))
+        refg = np.zeros((m, n), dtype=want.dtype)
         for r in range(P):
-            pl = MultiplyPlan(None, m, n, k, steps, "d", rank=r, nranks=P, allocate=False)
+            pl = MultiplyPlan(None, m, n, k, steps, dtype, rank=r, nranks=P, allocate=False)
             if r < len(ref_locals) and ref_locals[r] is not None and ref_locals[r].size == pl.initial_elements[2]:
                 gather_local_to_global(pl, "C", ref_locals[r], refg)
             pl.destroy()
         ref_right = bool(np.array_equal(refg, want))
         if ours_right and not ref_right:
             ref_wrong += 1
-            print("REFERENCE WRONG (ours equals the dense product)", m, n, k, P, steps, alpha, beta)
+            print("REFERENCE WRONG (ours equals the dense product)", dtype, m, n, k, P, steps, alpha, beta)
         else:
             bad += 1
-            print("MISMATCH", m, n, k, P, steps, alpha, beta, "ours right:", ours_right, "reference right:", ref_right)
+            print("MISMATCH", dtype, m, n, k, P, steps, alpha, beta, "ours right:", ours_right, "reference right:", ref_right)
     print("cases run %d, skipped (strategy rejected or reference crashed) %d, reference wrong %d, OUR mismatches %d" % (ran, skipped, ref_wrong, bad))
     return 1 if bad else 0
 
