@@ -18,6 +18,7 @@
 #include <stdexcept>
 #include <string>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <thread>
 #include <unistd.h>
 
@@ -85,6 +86,7 @@ void read_all(int fd, void* buf, std::size_t n) {
         if (r == 0) fail("peer closed the connection");
         if (r < 0) {
             if (errno == EINTR) continue;
+            if (errno == EAGAIN || errno == EWOULDBLOCK) fail("no message within COSMA_B200_PG_RECV_TIMEOUT seconds: giving up");
             fail(std::string("recv: ") + std::strerror(errno));
         }
         p += r;
@@ -95,6 +97,14 @@ void read_all(int fd, void* buf, std::size_t n) {
 void tune(int fd) {
     int one = 1;
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+    // COSMA_B200_PG_RECV_TIMEOUT [s] (unset: wait forever, like MPI): a rank that hears nothing for that long gives up instead of
+    // outliving a killed launcher -- test launchers set it so that a protocol error can never leave processes parked on the GPUs
+    const int limit = env_int("COSMA_B200_PG_RECV_TIMEOUT", 0);
+    if (limit > 0) {
+        timeval tv{};
+        tv.tv_sec = limit;
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    }
 }
 
 int listen_on(int port, int* bound_port) {
@@ -376,10 +386,13 @@ int recv_any(group* g, void* buf, std::size_t bytes, int tag) {
             who.push_back(w);
         }
         if (fds.empty()) fail("recv_any: nobody to receive from");
-        if (::poll(fds.data(), fds.size(), -1) < 0) {
+        const int limit = env_int("COSMA_B200_PG_RECV_TIMEOUT", 0);
+        const int ready = ::poll(fds.data(), fds.size(), limit > 0 ? limit * 1000 : -1);
+        if (ready < 0) {
             if (errno == EINTR) continue;
             fail(std::string("poll: ") + std::strerror(errno));
         }
+        if (ready == 0) fail("no message within COSMA_B200_PG_RECV_TIMEOUT seconds: giving up");
         for (size_t f = 0; f < fds.size(); ++f) {
             if (!(fds[f].revents & (POLLIN | POLLHUP))) continue;
             message m;

@@ -29,6 +29,8 @@ def launch(np_, argv, timeout=None, env_extra=None, capture=False):
         env = dict(os.environ)
         env.update({"RANK": str(r), "WORLD_SIZE": str(np_), "LOCAL_RANK": str(r), "MASTER_ADDR": "127.0.0.1",
                     "COSMA_B200_PG_PORT": str(port)})
+        if timeout:  # a rank that hears nothing for longer than the whole job may take gives up by itself (orphan protection)
+            env.setdefault("COSMA_B200_PG_RECV_TIMEOUT", str(int(timeout) + 30))
         if env_extra:
             env.update(env_extra)
         procs.append(subprocess.Popen(argv, env=env, stdout=subprocess.PIPE if capture else None,
