@@ -21,6 +21,17 @@ def free_port():
     return p
 
 
+def _child_setup():
+    """Own session (so the whole rank can be killed as a group) and SIGKILL when the launcher itself dies (PR_SET_PDEATHSIG): a rank must
+    never outlive the test run that started it and sit on a GPU."""
+    os.setsid()
+    try:
+        import ctypes
+        ctypes.CDLL(None).prctl(1, signal.SIGKILL)
+    except Exception:
+        pass
+
+
 def launch(np_, argv, timeout=None, env_extra=None, capture=False):
     """Returns (exit code, [stdout of each rank] if capture). Any failing rank takes the others down."""
     port = free_port()
@@ -34,7 +45,7 @@ def launch(np_, argv, timeout=None, env_extra=None, capture=False):
         if env_extra:
             env.update(env_extra)
         procs.append(subprocess.Popen(argv, env=env, stdout=subprocess.PIPE if capture else None,
-                                      stderr=subprocess.STDOUT if capture else None, start_new_session=True))
+                                      stderr=subprocess.STDOUT if capture else None, preexec_fn=_child_setup))
     t0 = time.time()
     code = 0
     live = set(range(np_))
