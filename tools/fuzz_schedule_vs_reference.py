@@ -40,7 +40,7 @@ def main():
     orc.ref()
     bad = ran = skipped = ref_wrong = 0
     for it in range(N):
-        P = rnd.choice([1, 2, 3, 4, 6, 8])
+        P = rnd.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 16])
         m, n, k = (rnd.randint(8, 120) for _ in range(3))
         mode = rnd.random()
         if mode < 0.5:
