@@ -34,6 +34,8 @@ void select_device();
 // The NCCL communicator of `comm` (all of its ranks), created collectively on first use -- rank 0 obtains the
 // ncclUniqueId and broadcasts it over `comm` as the reference does (src/cosma/gpu/nccl_utils.cpp:21-42) -- and cached by
 // communicator identity until release_comm / process exit (the reference caches per context, context.cpp:80-125).
+// Call release_comm(comm) before MPI_Comm_free(&comm): communicator identities (MPI_Comm_c2f handles with a real MPI) can be
+// handed out again after a free, and a stale cache entry would then be served for the new communicator.
 void* comm_handle(MPI_Comm comm);
 // The first P ranks of comm as a communicator of their own (comm itself when P == its size), created with
 // MPI_Comm_create_group -- collective over those P ranks only, like the reference's communicator (communicator.cpp:282-343)
