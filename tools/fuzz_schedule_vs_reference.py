@@ -47,6 +47,18 @@ def main():
             steps = random_steps(rnd, P)
         else:
             steps = ""
+        # a dimension divided into more parts than it has elements is meaningless in the reference (Interval::subinterval returns the whole
+        # interval, interval.cpp:84-98, so work is duplicated) and here alike: not a parity question
+        over = False
+        for dim, length in (("m", m), ("n", n), ("k", k)):
+            prod = 1
+            for st in steps.split(","):
+                if st and st[1] == dim:
+                    prod *= int(st[2:])
+            over = over or prod > length
+        if over:
+            skipped += 1
+            continue
         alpha, beta = rnd.choice([(1.0, 0.0), (1.0, 1.0), (2.0, -1.0)])
         rng = np.random.default_rng(it)
         dtype = rnd.choice("ddz")
