@@ -279,6 +279,19 @@ static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int 
                 strategy = cosma::parse_strategy(m, n, k, static_cast<size_t>(P), st);
             }
         }
+        // a dimension cut into more parts than it has elements: the reference accepts it and then computes garbage (Interval::subinterval
+        // hands out the whole interval when the divisor exceeds the length, interval.cpp:84-98); refuse instead of multiplying wrongly
+        {
+            long long parts[3] = {1, 1, 1};
+            for (size_t s = 0; s < strategy.n_steps(); ++s) parts[strategy.split_m(s) ? 0 : (strategy.split_n(s) ? 1 : 2)] *= strategy.divisor(s);
+            const long long dims[3] = {m, n, k};
+            for (int d = 0; d < 3; ++d)
+                if (parts[d] > dims[d] && dims[d] > 0) {
+                    set_last_error(std::string("the strategy divides dimension ") + "mnk"[d] + " = " + std::to_string(dims[d]) + " into " +
+                                   std::to_string(parts[d]) + " parts: not a meaningful decomposition (the reference computes a wrong product here)");
+                    return COSMA_B200_INVALID_ARG;
+                }
+        }
         auto plan = std::make_unique<Plan>();
         plan->schedule = cosma::Schedule(strategy, rank);
         plan->dtype = dtype;

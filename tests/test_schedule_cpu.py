@@ -72,3 +72,13 @@ def test_statistics_tool(lib, capsys):
     assert statistics.main(["-m", "8192", "-n", "8192", "-k", "1048576", "-P", "8"]) == 0
     out = capsys.readouterr().out
     assert "strategy  : pk8" in out and "reduce     C  ring of 8" in out
+
+
+def test_over_divided_dimension_is_refused(lib):
+    """m = 2 cut into 3 sequential parts: the reference's Strategy accepts it and its multiply then returns a wrong product
+    (Interval::subinterval returns the whole interval, interval.cpp:84-98). The plan refuses with a clear message instead."""
+    from cosma_b200.distributed import MultiplyPlan
+    with pytest.raises(Exception, match="divides dimension m = 2 into 3 parts"):
+        MultiplyPlan(None, 2, 14, 55, "sm3", "d", rank=0, nranks=1, allocate=False)
+    pl = MultiplyPlan(None, 3, 14, 55, "sm3", "d", rank=0, nranks=1, allocate=False)  # exactly one row per part is fine
+    pl.destroy()
