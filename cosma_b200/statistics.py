@@ -52,6 +52,25 @@ def describe(m, n, k, P, steps="", dtype="double", ranks=None):
             "flops": worst["flops"], "ops": worst["ops"], "t_gemm_ms": t_gemm * 1e3, "t_wire_ms": t_wire * 1e3}
 
 
+def layouts(m, n, k, P, steps=""):
+    """COSMA's native layout of A, B, C as grids (the reference's miniapp/layout_miniapp.cpp prints the same): row split points, column split
+    points and the owner rank of every block."""
+    from . import planning
+    full = steps or planning.strategy(m, n, k, P)[0]
+    P_used = planning.strategy(m, n, k, P, 0, full)[1] if full else 1
+    out = {}
+    for label, (rows, cols) in (("A", (m, k)), ("B", (k, n)), ("C", (m, n))):
+        per = planning.mapper_layout(label, m, n, k, P_used, full)
+        rs = sorted({b[0] for bl in per for b in bl} | {rows})
+        cs = sorted({b[2] for bl in per for b in bl} | {cols})
+        owners = [[-1] * (len(cs) - 1) for _ in range(len(rs) - 1)]
+        for r, bl in enumerate(per):
+            for (r0, r1, c0, c1) in bl:
+                owners[rs.index(r0)][cs.index(c0)] = r
+        out[label] = (rs, cs, owners)
+    return full, out
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="cosma_b200.statistics")
     ap.add_argument("-m", type=int, required=True)
@@ -60,6 +79,7 @@ def main(argv=None):
     ap.add_argument("-P", type=int, required=True)
     ap.add_argument("-s", "--steps", default="")
     ap.add_argument("-t", "--type", default="double", choices=sorted(BYTES))
+    ap.add_argument("--layout", action="store_true", help="also print the native layout grids of A, B, C (layout_miniapp)")
     a = ap.parse_args(argv)
     ranks = None if a.P <= 64 else [0, 1, a.P // 2, a.P - 1]
     d = describe(a.m, a.n, a.k, a.P, a.steps, a.type, ranks)
@@ -73,6 +93,15 @@ def main(argv=None):
     print("per rank (worst): device arenas %.2f GB, wire %.1f MB, GEMM %.2f TFLOP" % (d["arena_bytes"] / 1e9, d["wire_bytes"] / 1e6, d["flops"] / 1e12))
     print("estimate  : GEMM %.2f ms + collectives %.2f ms (not overlapped) -> %.1f %% of the step is communication" %
           (d["t_gemm_ms"], d["t_wire_ms"], 100.0 * d["t_wire_ms"] / max(d["t_gemm_ms"] + d["t_wire_ms"], 1e-12)))
+    if a.layout:
+        _, grids = layouts(a.m, a.n, a.k, a.P, a.steps)
+        for label in "ABC":
+            rs, cs, owners = grids[label]
+            print("layout of %s: row splits %s\n             col splits %s" % (label, rs, cs))
+            for row in owners[:16]:
+                print("             owners " + " ".join("%3d" % o for o in row[:32]) + (" ..." if len(row) > 32 else ""))
+            if len(owners) > 16:
+                print("             ... %d more block rows" % (len(owners) - 16))
     return 0
 
 
