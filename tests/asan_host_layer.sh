@@ -1,7 +1,7 @@
 #!/bin/bash
 # AddressSanitizer + UBSan over the whole C++ host layer on the CPU: the api/ and host/ sources, the CPU stand-in for the C ABI
 # (tests/cpp/mock_b200.cpp) and a test program are linked into ONE instrumented executable per program and run on several ranks.
-# Usage: tools/asan_host_layer.sh [outdir]   (takes a few minutes; last run: clean at 1-8 ranks)
+# Usage: tests/asan_host_layer.sh [outdir]   (takes a few minutes; last run: clean at 1-8 ranks)
 set -e
 R=$(cd "$(dirname "$0")/.." && pwd)
 OUT=${1:-/tmp/cosma_b200_asan}

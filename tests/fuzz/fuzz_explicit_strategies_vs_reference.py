@@ -1,8 +1,10 @@
 """Randomised parity of EXPLICIT step lists (random mixes of sequential and parallel steps, possibly invalid) through cosma_b200_strategy and the
 unmodified reference Strategy: acceptance / rejection and the validated strategy must agree. Last run: 3000 lists, 2713 accepted, 287 rejected by
-both, 0 disagreements.  python tools/fuzz_explicit_strategies_vs_reference.py"""
+both, 0 disagreements.  python tests/fuzz/fuzz_explicit_strategies_vs_reference.py"""
 import sys, ctypes, random, os
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tools')
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from cosma_b200 import _lib
 from oracle import oracle as orc
 from fuzz_schedule_vs_reference import random_steps

@@ -1,7 +1,7 @@
-"""Randomised parity of cosma_b200_mapper_layout against the unmodified reference Mapper: python tools/fuzz_mapper_vs_reference.py SEED N.
+"""Randomised parity of cosma_b200_mapper_layout against the unmodified reference Mapper: python tests/fuzz/fuzz_mapper_vs_reference.py SEED N.
 Last run: 2400 layouts (A, B, C of 800 random problems, P up to 64, memory-limited strategies included), 0 mismatches."""
 import sys, ctypes, random, os
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from cosma_b200 import _lib, planning
 from oracle import oracle as orc
 lib=_lib.load(); R=orc.ref()

@@ -3,14 +3,14 @@
       lock-step; every rank's local array must equal the reference's (costa::pxtran_op / costa::pxgemr2d) BIT FOR BIT, padding included;
   p?gemm: our three-phase pipeline (tests/test_pxgemm_cpu.py) against cosma::pxgemm of the reference, exact on integer matrices.
 Random matrix sizes, block sizes, process grids (both numberings), sub-matrix origins, rsrc/csrc, transposes, alpha/beta.
-    python tools/fuzz_scalapack_wrappers_vs_reference.py SEED N"""
+    python tests/fuzz/fuzz_scalapack_wrappers_vs_reference.py SEED N"""
 import os
 import random
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import costa_sim as sim  # noqa: E402
 from oracle import oracle as orc  # noqa: E402

@@ -1,6 +1,6 @@
 """Randomised distributed parity: random (m, n, k), rank counts and strategies (automatic, memory-limited, or random explicit step
 lists with sequential and parallel steps) run through the UNMODIFIED reference cosma::multiply on P minimpi ranks and through OUR
-compiled schedule in CPU lock-step; every rank's local C must be bit-identical (integer inputs). python tools/fuzz_schedule_vs_reference.py SEED N
+compiled schedule in CPU lock-step; every rank's local C must be bit-identical (integer inputs). python tests/fuzz/fuzz_schedule_vs_reference.py SEED N
 Last run: see DESIGN.md 5a."""
 import os
 import random
@@ -8,7 +8,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from cosma_b200 import planning  # noqa: E402
 from oracle import oracle as orc  # noqa: E402

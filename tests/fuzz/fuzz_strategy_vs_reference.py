@@ -1,7 +1,7 @@
-"""Randomised parity of cosma_b200_strategy against the unmodified reference Strategy (oracle/_ref): python tools/fuzz_strategy_vs_reference.py SEED N.
+"""Randomised parity of cosma_b200_strategy against the unmodified reference Strategy (oracle/_ref): python tests/fuzz/fuzz_strategy_vs_reference.py SEED N.
 Last run: 4000 cases (dims 1..300000, P 1..1024, 35 % with memory limits), 0 mismatches in steps, ranks used and memory_used."""
 import sys, ctypes, random, io, contextlib, os
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from cosma_b200 import _lib
 from oracle import oracle as orc
 lib=_lib.load(); R=orc.ref()

@@ -102,7 +102,7 @@ def test_committed_golden_fixture(planning):
 
 @pytest.mark.parametrize("seed", [11, 12])
 def test_randomised_strategy_and_mapper_parity(lib, ref, seed):
-    """A seeded slice of tools/fuzz_strategy_vs_reference.py / fuzz_mapper_vs_reference.py (4000 + 2400 cases offline, no mismatch):
+    """A seeded slice of tests/fuzz/fuzz_strategy_vs_reference.py / fuzz_mapper_vs_reference.py (4000 + 2400 cases offline, no mismatch):
     random shapes, rank counts and memory limits; steps, ranks used, memory_used and every rank's block list equal the reference's."""
     import ctypes
     import random

@@ -99,7 +99,7 @@ def test_committed_reference_fixtures(lib, name):
 
 
 def test_randomised_schedules_against_the_live_reference(lib, refd):
-    """A seeded slice of tools/fuzz_schedule_vs_reference.py (755 random problems offline: random shapes, 1-8 ranks, automatic or random
+    """A seeded slice of tests/fuzz/fuzz_schedule_vs_reference.py (755 random problems offline: random shapes, 1-8 ranks, automatic or random
     explicit strategies mixing sequential and parallel steps, three (alpha, beta) pairs): wherever the reference's answer is right, every
     rank's local C of our compiled schedule is bit-identical to it; the tool found NO case where ours is wrong, and 21 exotic explicit
     strategies (e.g. sm2,pm2,pm2 or pk2,sn2,pn2) where the REFERENCE's result differs from the dense product while ours
@@ -107,7 +107,7 @@ def test_randomised_schedules_against_the_live_reference(lib, refd):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_schedule_vs_reference.py"), "7", "25"], capture_output=True, text=True,
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz", "fuzz_schedule_vs_reference.py"), "7", "25"], capture_output=True, text=True,
                          timeout=900, cwd=root)
     tail = [ln for ln in out.stdout.splitlines() if ln.startswith("cases run")]
     assert out.returncode == 0 and tail and tail[0].endswith("OUR mismatches 0"), out.stdout[-3000:]
