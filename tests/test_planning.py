@@ -135,3 +135,48 @@ def test_randomised_strategy_and_mapper_parity(lib, ref, seed):
             assert ours == theirs, (label, m, n, k, P_used, steps)
             checked += 1
     assert checked > 100
+
+
+def test_reference_mapper_rpa_256(planning, ref):
+    """tests/mapper.cpp:6-35 (mapper, rpa_256): 34816 x 34816 x 13893632 on 1024 ranks with the explicit strategy sk2,sm2,pk512,pm2 -- every
+    rank's Mapper of A, B, C must construct (the reference needs ~7 s for its O(P^2) loops; here milliseconds) -- and the complete
+    layouts equal the unmodified reference's."""
+    import ctypes
+    import time
+    m = n = 34816
+    k, P, steps = 13893632, 1024, "sk2,sm2,pk512,pm2"
+    t0 = time.time()
+    ours = {label: planning.mapper_layout(label, m, n, k, P, steps) for label in "ABC"}
+    assert time.time() - t0 < 5.0
+    for label, (rows, cols) in (("A", (m, k)), ("B", (k, n)), ("C", (m, n))):
+        assert len(ours[label]) == P and all(len(b) >= 1 for b in ours[label])
+        assert sum((b[1] - b[0] + 1) * (b[3] - b[2] + 1) for bl in ours[label] for b in bl) == rows * cols
+    R = ref.ref()
+    for label in "ABC":
+        counts = (ctypes.c_int * P)()
+        flat = (ctypes.c_int * (4 * 100000))()
+        assert R.ref_mapper_layout(ctypes.c_char(label.encode()), m, n, k, P, steps.encode(), counts, flat, 4 * 100000) >= 0
+        pos, theirs = 0, []
+        for r in range(P):
+            theirs.append([tuple(flat[4 * (pos + b):4 * (pos + b) + 4]) for b in range(counts[r])])
+            pos += counts[r]
+        assert ours[label] == theirs
+
+
+def test_reference_strategy_nested_sequential_parallel(planning, ref):
+    """tests/mapper.cpp:63-80 (strategy, nested_sequential_parallel): 30000^3 on 360 ranks under 80e6 elements per rank. The reference only
+    prints it; here it must equal the reference's string and stay within the limit (which this size does without sequential
+    steps; a tighter limit that forces them is compared as well)."""
+    import ctypes
+    R = ref.ref()
+    out = ctypes.create_string_buffer(8192)
+    Po, mu = ctypes.c_int(0), ctypes.c_longlong(0)
+    assert R.ref_strategy(30000, 30000, 30000, 360, ctypes.c_longlong(80000000), b"", out, 8192, ctypes.byref(Po), ctypes.byref(mu)) >= 0
+    steps, P_used, mem = planning.strategy(30000, 30000, 30000, 360, 80000000)
+    assert (steps, P_used, mem) == (out.value.decode(), Po.value, mu.value)
+    assert mem <= 80000000
+    tight = (mem * 2) // 3
+    assert R.ref_strategy(30000, 30000, 30000, 360, ctypes.c_longlong(tight), b"", out, 8192, ctypes.byref(Po), ctypes.byref(mu)) >= 0
+    steps, P_used, mem = planning.strategy(30000, 30000, 30000, 360, tight)
+    assert (steps, P_used, mem) == (out.value.decode(), Po.value, mu.value)
+    assert any(s.startswith("s") for s in steps.split(",")) and mem <= tight
