@@ -21,6 +21,8 @@ miniapps: build
 	mkdir -p tests/cpp/bin
 	g++ -O2 -std=c++17 -I include miniapp/cosma_miniapp.cpp -o tests/cpp/bin/cosma_miniapp -L cosma_b200/lib -lcosma -lcosma_b200 -Wl,-rpath,$(CURDIR)/cosma_b200/lib
 	g++ -O2 -std=c++17 -I include miniapp/pxgemm_miniapp.cpp -o tests/cpp/bin/pxgemm_miniapp -L cosma_b200/lib -lcosma_pxgemm_cpp -lcosma_blacs_lite -lcosma -lcosma_b200 -Wl,-rpath,$(CURDIR)/cosma_b200/lib
+	g++ -O2 -std=c++17 -I include miniapp/pxgemr2d_miniapp.cpp -o tests/cpp/bin/pxgemr2d_miniapp -L cosma_b200/lib -lcosma_pxgemm_cpp -lcosma_blacs_lite -lcosma -lcosma_b200 -Wl,-rpath,$(CURDIR)/cosma_b200/lib
+	g++ -O2 -std=c++17 -I include miniapp/pxtran_miniapp.cpp -o tests/cpp/bin/pxtran_miniapp -L cosma_b200/lib -lcosma_pxgemm_cpp -lcosma_blacs_lite -lcosma -lcosma_b200 -Wl,-rpath,$(CURDIR)/cosma_b200/lib
 
 clean:
 	rm -rf cosma_b200/build cosma_b200/lib tests/cpp/bin oracle/_ref oracle/liboracle.so

@@ -29,6 +29,8 @@ PROGRAMS = {
     "test_pxgemm": (os.path.join(CPP, "test_pxgemm.cpp"), ["cosma_prefixed_pxgemm", "cosma_pxgemm", "cosma_pxgemm_cpp", "cosma_blacs_lite"], True),
     "cosma_miniapp": (os.path.join(ROOT, "miniapp", "cosma_miniapp.cpp"), [], False),
     "pxgemm_miniapp": (os.path.join(ROOT, "miniapp", "pxgemm_miniapp.cpp"), ["cosma_pxgemm_cpp", "cosma_blacs_lite"], False),
+    "pxgemr2d_miniapp": (os.path.join(ROOT, "miniapp", "pxgemr2d_miniapp.cpp"), ["cosma_pxgemm_cpp", "cosma_blacs_lite"], False),
+    "pxtran_miniapp": (os.path.join(ROOT, "miniapp", "pxtran_miniapp.cpp"), ["cosma_pxgemm_cpp", "cosma_blacs_lite"], False),
 }
 
 
@@ -42,7 +44,8 @@ def program(name, oracle=None):
     src, libs, needs_oracle = PROGRAMS[name]
     out = os.path.join(BIN, name)
     os.makedirs(BIN, exist_ok=True)
-    deps = [src] + [os.path.join(CPP, f) for f in os.listdir(CPP) if f.endswith(".hpp")] + [os.path.join(LIBDIR, "libcosma.so")]
+    deps = [src] + [os.path.join(d, f) for d in (CPP, os.path.join(ROOT, "miniapp")) for f in os.listdir(d) if f.endswith(".hpp")]
+    deps.append(os.path.join(LIBDIR, "libcosma.so"))
     if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(d) for d in deps):
         return out
     cmd = ["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", out, "-L", LIBDIR]
@@ -124,7 +127,8 @@ def test_host_layer_compiles_against_a_real_mpi_header(source):
 
 
 @pytest.mark.parametrize("source", ["tests/cpp/test_multiply.cpp", "tests/cpp/test_multiply_using_layout.cpp", "tests/cpp/test_pxgemm.cpp",
-                                    "tests/cpp/test_pxtran.cpp", "tests/cpp/test_costa_examples.cpp", "miniapp/cosma_miniapp.cpp", "miniapp/pxgemm_miniapp.cpp"])
+                                    "tests/cpp/test_pxtran.cpp", "tests/cpp/test_costa_examples.cpp", "miniapp/cosma_miniapp.cpp", "miniapp/pxgemm_miniapp.cpp",
+                                    "miniapp/pxgemr2d_miniapp.cpp", "miniapp/pxtran_miniapp.cpp"])
 def test_programs_compile_against_a_real_mpi_header(source):
     """The test programs and miniapps only use MPI calls that exist in MPI: they compile unchanged with -DCOSMA_B200_WITH_MPI."""
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-DCOSMA_B200_WITH_MPI", "-DMPI_Comm_c2f(c)=(c)", "-I", os.path.join(ROOT, "include"),
@@ -244,6 +248,30 @@ def test_pxgemm_miniapp_multirank_on_cpu(host_libs):
     assert "COSMA TIMES [ms] =" in out and "grid 2 x 3" in out, out
 
 
+@pytest.mark.parametrize("np_,args", [
+    (1, ["-m", "100", "-n", "77", "--block_a", "16,8", "--block_c", "5,32"]),
+    (6, ["-m", "301", "-n", "203", "--block_a", "32,16", "--block_c", "7,50", "-p", "2,3", "-q", "3,2", "-t", "zdouble"]),
+    (6, ["-m", "128", "-n", "256", "--block_a", "32,32", "--block_c", "32,32", "-p", "2,2", "-q", "1,6", "-t", "float"]),   # grid A leaves ranks out
+    (4, ["-m", "90", "-n", "90", "--block_a", "9,9", "--block_c", "10,10", "-p", "3,3", "-t", "zfloat"]),                 # wrong grid -> 1 x P
+])
+def test_pxgemr2d_miniapp_multirank_on_cpu(host_libs, np_, args):
+    """libs/COSTA/miniapps/pxgemr2d_miniapp.cpp's counterpart with --test: every rank checks its part of C against the definition."""
+    out = _run_on_mock(np_, [program("pxgemr2d_miniapp")] + args + ["--test"])
+    assert "COSTA TIMES [ms] =" in out and "Result is CORRECT!" in out, out
+
+
+@pytest.mark.parametrize("np_,args", [
+    (1, ["-m", "60", "-n", "45", "--block_a", "8,8", "--block_c", "16,4"]),
+    (6, ["-m", "301", "-n", "203", "--block_a", "32,16", "--block_c", "7,50", "-p", "2,3", "-t", "zdouble", "--op", "C", "--alpha", "2", "--beta", "-1"]),
+    (4, ["-m", "128", "-n", "64", "--block_a", "32,32", "--block_c", "32,32", "-t", "float", "--alpha", "3"]),
+    (4, ["-m", "50", "-n", "70", "--block_a", "3,5", "--block_c", "4,6", "-t", "zfloat", "--beta", "1"]),
+])
+def test_pxtran_miniapp_multirank_on_cpu(host_libs, np_, args):
+    """libs/COSTA/miniapps/pxtran_miniapp.cpp's counterpart with --test (transpose / conjugate transpose, integer alpha and beta)."""
+    out = _run_on_mock(np_, [program("pxtran_miniapp")] + args + ["--test"])
+    assert "COSTA TIMES [ms] =" in out and "Result is CORRECT!" in out, out
+
+
 # ---- GPU --------------------------------------------------------------------------------------------------------------
 
 def _gpus():
@@ -291,3 +319,16 @@ def test_pxgemm_miniapp(host_libs, np_):
     out = run_ranks(np_, [program("pxgemm_miniapp"), "-m", "1024", "-n", "768", "-k", "512", "--block_a", "128,128", "--block_b", "64,64",
                           "--block_c", "128,32", "--trans_a", "T", "-r", "2", "--type", "zdouble"], timeout=120)
     assert "COSMA TIMES [ms] =" in out, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("np_", [1, 2, 4, 8])
+@pytest.mark.parametrize("dtype", ["double", "zfloat"])
+def test_costa_miniapps(host_libs, dtype, np_):
+    """p?gemr2d and p?tran(c) miniapps with --test: host-resident block-cyclic arrays, exact check on every rank."""
+    _skip_unless_ranks(np_)
+    out = run_ranks(np_, [program("pxgemr2d_miniapp"), "-m", "1500", "-n", "1100", "--block_a", "128,64", "--block_c", "50,200", "-t", dtype, "--test"], timeout=120)
+    assert "Result is CORRECT!" in out, out
+    out = run_ranks(np_, [program("pxtran_miniapp"), "-m", "1500", "-n", "1100", "--block_a", "128,64", "--block_c", "50,200", "-t", dtype, "--op", "C",
+                          "--alpha", "2", "--beta", "-1", "--test"], timeout=120)
+    assert "Result is CORRECT!" in out, out
