@@ -26,17 +26,18 @@ static bool run(const params& p, int ctxt, std::vector<double>& times) {
     cosma::memory_pool<T> pool;
     block_cyclic_matrix<T> A(pool, ctxt, p.n, p.m, p.ba[0], p.ba[1]), C(pool, ctxt, p.m, p.n, p.bc[0], p.bc[1]);
     const T alpha = static_cast<T>(p.alpha), beta = static_cast<T>(p.beta);
+    const char op = sizeof(T) == sizeof(typename real_of<T>::type) ? 'T' : p.op;  // real types: p?tran
     A.fill([](long long i, long long j) { return element<T>(0, i, j); });
     for (int r = 0; r < p.n_rep; ++r) {
         C.fill([](long long i, long long j) { return element<T>(1, i, j); });
         MPI_Barrier(MPI_COMM_WORLD);
         const auto t0 = std::chrono::steady_clock::now();
-        costa::pxtran_op<T>(p.m, p.n, alpha, A.data(), 1, 1, A.desc, beta, C.data(), 1, 1, C.desc, p.op);
+        costa::pxtran_op<T>(p.m, p.n, alpha, A.data(), 1, 1, A.desc, beta, C.data(), 1, 1, C.desc, op);
         MPI_Barrier(MPI_COMM_WORLD);
         times.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     }
     if (!p.test) return true;
-    const bool conj = p.op == 'C';
+    const bool conj = op == 'C';
     return C.mismatches([&](long long i, long long j) { return beta * element<T>(1, i, j) + alpha * conj_if(element<T>(0, j, i), conj); }) == 0;
 }
 
