@@ -25,6 +25,7 @@ struct Comm {
     // communicator + strategy in its context, context.cpp:80-125); destroyed with the communicator
     std::map<std::string, LayoutMultiplyState*> layout_states;
     LayoutMultiplyState* last_layout_state = nullptr;
+    unsigned long long layout_state_clock = 0;  // use counter for the least-recently-used bound on layout_states
     ~Comm();
 };
 

@@ -17,6 +17,7 @@
 #include <costa/erased_layout.hpp>
 #include <costa/grid2grid/comm_volume.hpp>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -43,6 +44,8 @@ struct LayoutMultiplyState {
     // communicator re-split with key perm[rank]; identity -> relabelled == nullptr and the plan runs on the parent
     std::vector<int> perm;
     Comm* relabelled = nullptr;
+    std::uint64_t last_used = 0;    // per-communicator call counter at the last use (least recently used state is dropped first)
+    std::uint64_t share_bytes = 0;  // (|A| + |B| + |C|) / ranks: the rank-independent size the cache bound counts
     ~LayoutMultiplyState() {
         transforms.clear();
         for (auto& e : ev)
@@ -184,6 +187,25 @@ bool relabelling_enabled() {
     return on;
 }
 
+// how many problems (dtype, m, n, k, strategy, relabelling) keep their plan and arenas per communicator
+size_t max_cached_problems() {
+    static const size_t n = [] {
+        const char* v = std::getenv("COSMA_B200_CACHED_PROBLEMS");
+        const long long x = v && *v ? std::atoll(v) : 64;
+        return static_cast<size_t>(x < 1 ? 1 : x);
+    }();
+    return n;
+}
+// ... and how many bytes of matrices per rank they may stand for together (COSMA_B200_CACHED_PROBLEMS_MB, default 32 GiB of 180 GB)
+std::uint64_t max_cached_bytes() {
+    static const std::uint64_t n = [] {
+        const char* v = std::getenv("COSMA_B200_CACHED_PROBLEMS_MB");
+        const long long x = v && *v ? std::atoll(v) : 32768;
+        return static_cast<std::uint64_t>(x < 0 ? 0 : x) << 20;
+    }();
+    return n;
+}
+
 // perm: this rank plays COSMA rank perm[rank] (an involution; empty or identity = no relabelling)
 int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, const std::vector<int>& perm, LayoutMultiplyState** out) {
     std::string key = std::string(1, dtype) + ":" + std::to_string(m) + ":" + std::to_string(n) + ":" + std::to_string(k) + ":" + (steps ? steps : "");
@@ -195,11 +217,32 @@ int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, const
     }
     auto it = c->layout_states.find(key);
     if (it != c->layout_states.end()) {
+        it->second->last_used = ++c->layout_state_clock;
         *out = it->second;
         return COSMA_B200_OK;
     }
+    // bounded cache: every state owns three device arenas and a set of ring communicators, so an application that walks through many
+    // shapes (the reference keeps ONE strategy per context and replans, context.cpp:80-125) must not accumulate them. Bounds: a
+    // number of problems and a number of bytes, the latter counted as the three matrices' share per rank -- a figure that is the
+    // same on every rank; every rank makes the same calls in the same order, so every rank drops the same states.
+    const std::uint64_t share = static_cast<std::uint64_t>((static_cast<double>(m) * k + static_cast<double>(k) * n + static_cast<double>(m) * n) *
+                                                           dtype_bytes(dtype) / std::max(c->size, 1));
+    for (;;) {
+        std::uint64_t held = 0;
+        for (const auto& kv : c->layout_states) held += kv.second->share_bytes;
+        if (c->layout_states.empty() || (c->layout_states.size() < max_cached_problems() && held + share <= max_cached_bytes())) break;
+        auto oldest = c->layout_states.begin();
+        for (auto jt = c->layout_states.begin(); jt != c->layout_states.end(); ++jt)
+            if (jt->second->last_used < oldest->second->last_used) oldest = jt;
+        COSMA_B200_CUDA_TRY(cudaDeviceSynchronize());  // its last multiply may still be queued
+        if (c->last_layout_state == oldest->second) c->last_layout_state = nullptr;
+        delete oldest->second;
+        c->layout_states.erase(oldest);
+    }
     auto st = std::make_unique<LayoutMultiplyState>();
     st->dtype = dtype;
+    st->last_used = ++c->layout_state_clock;
+    st->share_bytes = share;
     Comm* pc = c;  // the communicator the multiply runs on
     if (relabel) {
         st->perm = perm;

@@ -3,7 +3,11 @@ run LAST in the suite so that a surprise here cannot hide the established kernel
 
 COSMA_B200_REPACK_UNALIGNED=ON: operands the TMA path cannot address (odd leading dimension, 8-byte-aligned base) are repacked once
 into a stream-ordered scratch and the tensor-pipe kernel runs on the copies (csrc/repack.h). Must give the same numbers as the
-oracle and report the tensor-pipe path (last_gemm_path == 1) where the default build reports the generic kernel (2)."""
+oracle and report the tensor-pipe path (last_gemm_path == 1) where the default build reports the generic kernel (2).
+
+COSMA_B200_CACHED_PROBLEMS=2: the per-communicator cache of p?gemm / multiply_using_layout problems (plan + three device arenas each)
+drops the least recently used problem; walking twice through six shapes must keep giving the dense result and must not accumulate
+device memory."""
 import os
 import subprocess
 import sys
@@ -63,3 +67,55 @@ def test_unaligned_operands_default_generic_kernel(lib, oracle):
 def test_unaligned_operands_repacked_onto_the_tensor_pipe(lib, oracle):
     code, text = _run("ON", 1)
     assert code == 0 and "RESULT OK" in text, text[-3000:]
+
+
+CACHE_SCRIPT = r'''
+import sys
+import torch
+sys.path.insert(0, %(root)r)
+from cosma_b200 import costa
+from cosma_b200.distributed import init_comm
+comm = init_comm()
+grid = costa.Grid(comm, "R", 1, 1)
+gen = torch.Generator(device="cuda").manual_seed(11)
+
+
+def one(m, n, k):
+    # column-major m x k etc. held as the transposed row-major tensors
+    At = torch.randint(-4, 5, (k, m), generator=gen, device="cuda").double()
+    Bt = torch.randint(-4, 5, (n, k), generator=gen, device="cuda").double()
+    Ct = torch.full((n, m), float("nan"), dtype=torch.float64, device="cuda")
+    desc = lambda r, c: [1, 0, r, c, 64, 32, 0, 0, r]
+    costa.pxgemm(grid, "d", "N", "N", m, n, k, 1.0, At.data_ptr(), 1, 1, desc(m, k), Bt.data_ptr(), 1, 1, desc(k, n), 0.0, Ct.data_ptr(), 1, 1, desc(m, n))
+    torch.cuda.synchronize()
+    return bool(torch.equal(Ct, Bt @ At))   # small integers: exact
+
+
+def free_bytes():
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return torch.cuda.mem_get_info()[0]
+
+
+ok = one(256, 256, 256)                      # loads the kernels, cuBLAS for the check
+base = free_bytes()
+# (|A| + |B| + |C|) * 8 B: 201, 168, 168, 159, 159, 168 MB -> 1023 MB if every problem stayed cached, <= 369 MB for any two
+shapes = [(4096, 4096, 1024), (4096, 2048, 2048), (2048, 4096, 2048), (3072, 4096, 1024), (4096, 3072, 1024), (2048, 2048, 4096)]
+for rep in range(2):
+    for (m, n, k) in shapes:
+        same = one(m, n, k)
+        ok = ok and same
+        print(rep, m, n, k, "exact", same)
+    held = base - free_bytes()
+    print("pass", rep, "device memory held by the library: %%.0f MB" %% (held / 2**20))
+    ok = ok and held < (700 << 20)
+print("RESULT", "OK" if ok else "FAILED")
+'''
+
+
+@pytest.mark.gpu
+def test_problem_cache_is_bounded(lib):
+    env = dict(os.environ, COSMA_B200_CACHED_PROBLEMS="2")
+    out = subprocess.run([sys.executable, "-c", CACHE_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    text = out.stdout + out.stderr
+    assert out.returncode == 0 and "RESULT OK" in text, text[-3000:]
