@@ -2,6 +2,7 @@
 #include "../../include/cosma_b200.h"
 #include "gemm_f64_sm100.h"
 #include "gemm_tf32x3_sm100.h"
+#include "exec_internal.h"
 
 #include <string>
 
@@ -53,15 +54,19 @@ int cosma_b200_cgemm(void* stream, char transa, char transb, int64_t m, int64_t 
 
 int cosma_b200_dgemm_host(void* stream, int64_t m, int64_t n, int64_t k, const double* alpha, const double* A, int64_t lda,
                           const double* B, int64_t ldb, const double* beta, double* C, int64_t ldc) {
-    if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
-    return cosma_b200::gemm_f64_host(static_cast<cudaStream_t>(stream), 1, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
-                                     &g_last_launches);
+    return cosma_b200::guarded("cosma_b200_dgemm_host", [&]() -> int {
+        if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
+        return cosma_b200::gemm_f64_host(static_cast<cudaStream_t>(stream), 1, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
+                                         &g_last_launches);
+    });
 }
 int cosma_b200_zgemm_host(void* stream, int64_t m, int64_t n, int64_t k, const double* alpha, const double* A, int64_t lda,
                           const double* B, int64_t ldb, const double* beta, double* C, int64_t ldc) {
-    if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
-    return cosma_b200::gemm_f64_host(static_cast<cudaStream_t>(stream), 2, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
-                                     &g_last_launches);
+    return cosma_b200::guarded("cosma_b200_zgemm_host", [&]() -> int {
+        if (!alpha || !beta) return COSMA_B200_INVALID_ARG;
+        return cosma_b200::gemm_f64_host(static_cast<cudaStream_t>(stream), 2, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc,
+                                         &g_last_launches);
+    });
 }
 int cosma_b200_last_launch_count(void) { return g_last_launches; }
 

@@ -9,6 +9,8 @@
 #include <costa/transform_plan.hpp>
 
 #include <map>
+#include <new>
+#include <stdexcept>
 #include <memory>
 #include <string>
 #include <vector>
@@ -81,6 +83,23 @@ int transform_plan_run(TransformPlan& plan, cudaStream_t stream);
             return COSMA_B200_NCCL_ERROR;                                                                \
         }                                                                                                \
     } while (0)
+// No C++ exception may cross the C ABI: entry points whose body can throw (std::bad_alloc, a Mapper asked for a rank it does
+// not have, ...) run inside guarded(), which turns the exception into a status + cosma_b200_last_error().
+template <typename F>
+int guarded(const char* what, F&& body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        try { set_last_error(std::string(what) + ": out of host memory"); } catch (...) {}
+        return COSMA_B200_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        try { set_last_error(std::string(what) + ": " + e.what()); } catch (...) {}
+        return COSMA_B200_INVALID_ARG;
+    } catch (...) {
+        return COSMA_B200_INTERNAL_ERROR;
+    }
+}
+
 #define COSMA_B200_CUDA_TRY(call)                                                                        \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \

@@ -430,16 +430,18 @@ int cosma_b200_zmultiply_using_layout(void* comm, const char* transa, const char
 }
 
 int cosma_b200_last_layout_multiply_stats(void* comm, float* ms3, int64_t* elements4, char* strategy, int strategy_len, int* launches) {
-    Comm* c = static_cast<Comm*>(comm);
-    if (!c || !c->last_layout_state) return COSMA_B200_INVALID_ARG;
-    LayoutMultiplyState* st = c->last_layout_state;
-    if (ms3)
-        for (int i = 0; i < 3; ++i)
-            if (cudaEventElapsedTime(&ms3[i], st->ev[i], st->ev[i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
-    if (elements4) std::memcpy(elements4, st->last_elements, sizeof(st->last_elements));
-    if (strategy) cosma_b200_plan_strategy(st->plan, strategy, strategy_len, nullptr);
-    if (launches) *launches = st->last_launches;
-    return COSMA_B200_OK;
+    return guarded("cosma_b200_last_layout_multiply_stats", [&]() -> int {
+        Comm* c = static_cast<Comm*>(comm);
+        if (!c || !c->last_layout_state) return COSMA_B200_INVALID_ARG;
+        LayoutMultiplyState* st = c->last_layout_state;
+        if (ms3)
+            for (int i = 0; i < 3; ++i)
+                if (cudaEventElapsedTime(&ms3[i], st->ev[i], st->ev[i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+        if (elements4) std::memcpy(elements4, st->last_elements, sizeof(st->last_elements));
+        if (strategy) cosma_b200_plan_strategy(st->plan, strategy, strategy_len, nullptr);
+        if (launches) *launches = st->last_launches;
+        return COSMA_B200_OK;
+    });
 }
 
 int cosma_b200_smultiply_using_layout(void* comm, const char* transa, const char* transb, const double* alpha,
@@ -454,35 +456,39 @@ int cosma_b200_cmultiply_using_layout(void* comm, const char* transa, const char
 }
 
 int cosma_b200_grid_create(void* comm, char order, int nprow, int npcol, void** grid_out) {
-    Comm* c = static_cast<Comm*>(comm);
-    if (!c || !grid_out || nprow < 1 || npcol < 1 || nprow * npcol > c->size) {
-        set_last_error("grid_create: need a communicator and nprow*npcol <= its size");
-        return COSMA_B200_INVALID_ARG;
-    }
-    order = std::toupper(order);
-    if (order != 'R' && order != 'C') return COSMA_B200_INVALID_ARG;
-    auto* g = new Grid;
-    g->comm = c;
-    g->order = order;
-    g->nprow = nprow;
-    g->npcol = npcol;
-    *grid_out = g;
-    return COSMA_B200_OK;
+    return guarded("cosma_b200_grid_create", [&]() -> int {
+        Comm* c = static_cast<Comm*>(comm);
+        if (!c || !grid_out || nprow < 1 || npcol < 1 || nprow * npcol > c->size) {
+            set_last_error("grid_create: need a communicator and nprow*npcol <= its size");
+            return COSMA_B200_INVALID_ARG;
+        }
+        order = std::toupper(order);
+        if (order != 'R' && order != 'C') return COSMA_B200_INVALID_ARG;
+        auto* g = new Grid;
+        g->comm = c;
+        g->order = order;
+        g->nprow = nprow;
+        g->npcol = npcol;
+        *grid_out = g;
+        return COSMA_B200_OK;
+    });
 }
 int cosma_b200_grid_destroy(void* grid) {
     delete static_cast<Grid*>(grid);
     return COSMA_B200_OK;
 }
 int cosma_b200_grid_info(void* grid, int* nprow, int* npcol, int* myrow, int* mycol) {
-    Grid* g = static_cast<Grid*>(grid);
-    if (!g) return COSMA_B200_INVALID_ARG;
-    if (nprow) *nprow = g->nprow;
-    if (npcol) *npcol = g->npcol;
-    int r = -1, cc = -1;
-    if (g->comm->rank < g->nprow * g->npcol) costa::rank_to_grid(g->comm->rank, g->nprow, g->npcol, g->order, &r, &cc);
-    if (myrow) *myrow = r;
-    if (mycol) *mycol = cc;
-    return COSMA_B200_OK;
+    return guarded("cosma_b200_grid_info", [&]() -> int {
+        Grid* g = static_cast<Grid*>(grid);
+        if (!g) return COSMA_B200_INVALID_ARG;
+        if (nprow) *nprow = g->nprow;
+        if (npcol) *npcol = g->npcol;
+        int r = -1, cc = -1;
+        if (g->comm->rank < g->nprow * g->npcol) costa::rank_to_grid(g->comm->rank, g->nprow, g->npcol, g->order, &r, &cc);
+        if (myrow) *myrow = r;
+        if (mycol) *mycol = cc;
+        return COSMA_B200_OK;
+    });
 }
 
 // descriptor fields (reference scalapack.hpp:11-47): [2] M, [3] N, [4] MB, [5] NB, [6] RSRC, [7] CSRC, [8] LLD

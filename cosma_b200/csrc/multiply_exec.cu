@@ -194,39 +194,44 @@ using cosma_b200::Comm;
 using cosma_b200::Plan;
 using cosma_b200::nccl;
 using cosma_b200::set_last_error;
+using cosma_b200::guarded;
 
 extern "C" {
 
 int cosma_b200_nccl_unique_id(uint8_t* out128) {
-    const auto* N = nccl();
-    if (!N) return COSMA_B200_NCCL_ERROR;
-    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-    ncclUniqueId id;
-    if (N->GetUniqueId(&id) != ncclSuccess) return COSMA_B200_NCCL_ERROR;
-    std::memcpy(out128, &id, 128);
-    return COSMA_B200_OK;
+    return guarded("cosma_b200_nccl_unique_id", [&]() -> int {
+        const auto* N = nccl();
+        if (!N) return COSMA_B200_NCCL_ERROR;
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        ncclUniqueId id;
+        if (N->GetUniqueId(&id) != ncclSuccess) return COSMA_B200_NCCL_ERROR;
+        std::memcpy(out128, &id, 128);
+        return COSMA_B200_OK;
+    });
 }
 
 int cosma_b200_comm_create(int rank, int nranks, const uint8_t* id128, void** comm_out) {
-    if (!comm_out || nranks < 1 || rank < 0 || rank >= nranks) return COSMA_B200_INVALID_ARG;
-    auto c = std::make_unique<Comm>();
-    c->rank = rank;
-    c->size = nranks;
-    if (nranks == 1) {  // single-rank job: nothing to exchange, NCCL is not needed (id128 may be NULL)
+    return guarded("cosma_b200_comm_create", [&]() -> int {
+        if (!comm_out || nranks < 1 || rank < 0 || rank >= nranks) return COSMA_B200_INVALID_ARG;
+        auto c = std::make_unique<Comm>();
+        c->rank = rank;
+        c->size = nranks;
+        if (nranks == 1) {  // single-rank job: nothing to exchange, NCCL is not needed (id128 may be NULL)
+            *comm_out = c.release();
+            return COSMA_B200_OK;
+        }
+        const auto* N = nccl();
+        if (!N || !id128) return COSMA_B200_NCCL_ERROR;
+        ncclUniqueId id;
+        std::memcpy(&id, id128, 128);
+        ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
+        if (r != ncclSuccess) {
+            set_last_error(std::string("ncclCommInitRank: ") + N->GetErrorString(r));
+            return COSMA_B200_NCCL_ERROR;
+        }
         *comm_out = c.release();
         return COSMA_B200_OK;
-    }
-    const auto* N = nccl();
-    if (!N || !id128) return COSMA_B200_NCCL_ERROR;
-    ncclUniqueId id;
-    std::memcpy(&id, id128, 128);
-    ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
-    if (r != ncclSuccess) {
-        set_last_error(std::string("ncclCommInitRank: ") + N->GetErrorString(r));
-        return COSMA_B200_NCCL_ERROR;
-    }
-    *comm_out = c.release();
-    return COSMA_B200_OK;
+    });
 }
 
 int cosma_b200_comm_destroy(void* comm) {
@@ -339,52 +344,73 @@ int cosma_b200_plan_destroy(void* plan) {
     return COSMA_B200_OK;
 }
 
+static bool valid_matrix(int matrix) { return matrix >= 0 && matrix <= 2; }
+
 int64_t cosma_b200_plan_arena_elements(void* plan, int matrix) {
+    if (!plan || !valid_matrix(matrix)) return -1;
     return static_cast<Plan*>(plan)->schedule.arena_elements(matrix);
 }
 int64_t cosma_b200_plan_initial_elements(void* plan, int matrix) {
+    if (!plan || !valid_matrix(matrix)) return -1;
     return static_cast<Plan*>(plan)->schedule.initial_elements(matrix);
 }
 int cosma_b200_plan_strategy(void* plan, char* out, int out_len, int* P_used) {
-    const auto& st = static_cast<Plan*>(plan)->schedule.strategy();
-    const std::string s = st.to_string();
-    if (static_cast<int>(s.size()) + 1 > out_len) return COSMA_B200_INVALID_ARG;
-    std::strcpy(out, s.c_str());
-    if (P_used) *P_used = static_cast<int>(st.P);
-    return COSMA_B200_OK;
+    if (!plan || !out) return COSMA_B200_INVALID_ARG;
+    return guarded("cosma_b200_plan_strategy", [&] {
+        const auto& st = static_cast<Plan*>(plan)->schedule.strategy();
+        const std::string s = st.to_string();
+        if (static_cast<int>(s.size()) + 1 > out_len) return static_cast<int>(COSMA_B200_INVALID_ARG);
+        std::strcpy(out, s.c_str());
+        if (P_used) *P_used = static_cast<int>(st.P);
+        return static_cast<int>(COSMA_B200_OK);
+    });
 }
 double cosma_b200_plan_gemm_flops(void* plan) {
     Plan* p = static_cast<Plan*>(plan);
+    if (!p) return 0.0;
     return p->schedule.total_gemm_flops() * (p->elem_reals == 2 ? 4.0 : 1.0);
 }
 int cosma_b200_plan_export(void* plan, int64_t* buf, int64_t cap, int64_t* len) {
-    const auto v = static_cast<Plan*>(plan)->schedule.serialize();
-    *len = static_cast<int64_t>(v.size());
-    if (buf && cap >= *len) std::memcpy(buf, v.data(), v.size() * sizeof(int64_t));
-    return COSMA_B200_OK;
+    if (!plan || !len) return COSMA_B200_INVALID_ARG;
+    return guarded("cosma_b200_plan_export", [&] {
+        const auto v = static_cast<Plan*>(plan)->schedule.serialize();
+        *len = static_cast<int64_t>(v.size());
+        if (buf && cap >= *len) std::memcpy(buf, v.data(), v.size() * sizeof(int64_t));
+        return static_cast<int>(COSMA_B200_OK);
+    });
 }
 int cosma_b200_plan_local_blocks(void* plan, int matrix, int rank, int* out, int cap, int* n_blocks) {
-    const auto& blocks = static_cast<Plan*>(plan)->schedule.mapper(matrix).initial_layout(rank);
-    *n_blocks = static_cast<int>(blocks.size());
-    if (out && cap >= 4 * *n_blocks)
-        for (int i = 0; i < *n_blocks; ++i) {
-            out[4 * i] = blocks[i].rows.first(); out[4 * i + 1] = blocks[i].rows.last();
-            out[4 * i + 2] = blocks[i].cols.first(); out[4 * i + 3] = blocks[i].cols.last();
+    if (!plan || !n_blocks || !valid_matrix(matrix)) return COSMA_B200_INVALID_ARG;
+    return guarded("cosma_b200_plan_local_blocks", [&] {
+        const cosma::Schedule& sch = static_cast<Plan*>(plan)->schedule;
+        if (rank < 0 || rank >= static_cast<int>(sch.strategy().P)) {  // ranks the strategy leaves idle own nothing
+            *n_blocks = 0;
+            return static_cast<int>(COSMA_B200_OK);
         }
-    return COSMA_B200_OK;
+        const auto& blocks = sch.mapper(matrix).initial_layout(rank);
+        *n_blocks = static_cast<int>(blocks.size());
+        if (out && cap >= 4 * *n_blocks)
+            for (int i = 0; i < *n_blocks; ++i) {
+                out[4 * i] = blocks[i].rows.first(); out[4 * i + 1] = blocks[i].rows.last();
+                out[4 * i + 2] = blocks[i].cols.first(); out[4 * i + 3] = blocks[i].cols.last();
+            }
+        return static_cast<int>(COSMA_B200_OK);
+    });
 }
 
 int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, void* A, void* B, void* C, void* stream) {
-    Plan* p = static_cast<Plan*>(plan);
-    if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
-    if (p->schedule.idle()) return COSMA_B200_OK;
-    bool needs_comm = false;
-    for (const auto& op : p->schedule.ops()) needs_comm |= op.kind != cosma::OpKind::GEMM;
-    if (needs_comm && p->ring_comms.empty()) {
-        set_last_error("plan was created without a communicator (plan-only); cannot execute collectives");
-        return COSMA_B200_INVALID_ARG;
-    }
-    return cosma_b200::plan_run(*p, alpha, beta, A, B, C, static_cast<cudaStream_t>(stream), nullptr);
+    return guarded("cosma_b200_multiply", [&]() -> int {
+        Plan* p = static_cast<Plan*>(plan);
+        if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
+        if (p->schedule.idle()) return COSMA_B200_OK;
+        bool needs_comm = false;
+        for (const auto& op : p->schedule.ops()) needs_comm |= op.kind != cosma::OpKind::GEMM;
+        if (needs_comm && p->ring_comms.empty()) {
+            set_last_error("plan was created without a communicator (plan-only); cannot execute collectives");
+            return COSMA_B200_INVALID_ARG;
+        }
+        return cosma_b200::plan_run(*p, alpha, beta, A, B, C, static_cast<cudaStream_t>(stream), nullptr);
+    });
 }
 
 /* Host-pointer variant: local A, B (and C when beta != 0) are uploaded from (pinned) host memory into arenas owned by
@@ -393,62 +419,64 @@ int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, voi
  * (src/cosma/local_multiply.cpp:341-363, gpu/nccl_utils.cpp:98,124-135). */
 int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta, const void* A, const void* B, void* C,
                              void* stream) {
-    Plan* p = static_cast<Plan*>(plan);
-    if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
-    if (p->schedule.idle()) return COSMA_B200_OK;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t es = static_cast<size_t>(p->elem_bytes());
-    for (int x = 0; x < 3; ++x)
-        if (!p->owned[x]) {
-            const size_t bytes = std::max<size_t>(p->schedule.arena_elements(x), 1) * es;
-            if (cudaMalloc(reinterpret_cast<void**>(&p->owned[x]), bytes) != cudaSuccess) {
-                set_last_error("cudaMalloc of a plan arena failed");
-                return COSMA_B200_OUT_OF_MEMORY;
-            }
-        }
-    const bool beta_zero = beta[0] == 0.0 && (p->elem_reals == 1 || beta[1] == 0.0);
-    // A schedule with ONE base-case GEMM that reads a local matrix as the caller holds it (no allgather of that matrix
-    // before it) / leaves local C as the caller wants it (no reduce after it) streams that matrix over PCIe under the
-    // kernel instead of copying it up front (host_gemm.cu): P = 1, and the un-gathered operands of P > 1 strategies
-    // (pk2 at P = 2: A and B; pn2,pk2 at P = 4: B; pk8 of the large-K config: A and B).
-    const cosma::ScheduleOp* gemm_op = nullptr;
-    int n_gemm = 0;
-    bool gathered[3] = {false, false, false};
-    for (const auto& op : p->schedule.ops()) {
-        if (op.kind == cosma::OpKind::GEMM) { gemm_op = &op; ++n_gemm; }
-        else gathered[op.matrix] = true;
-    }
-    cosma_b200::HostOperands hs;
-    bool streamed[3] = {false, false, false};
-    if (n_gemm == 1) {
-        const auto& g = *gemm_op;
-        const int64_t need[3] = {int64_t(g.m) * g.k, int64_t(g.k) * g.n, int64_t(g.m) * g.n};
-        const int64_t off[3] = {g.a_off, g.b_off, g.c_off};
+    return guarded("cosma_b200_multiply_host", [&]() -> int {
+        Plan* p = static_cast<Plan*>(plan);
+        if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
+        if (p->schedule.idle()) return COSMA_B200_OK;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const size_t es = static_cast<size_t>(p->elem_bytes());
         for (int x = 0; x < 3; ++x)
-            streamed[x] = !gathered[x] && off[x] == 0 && need[x] == p->schedule.initial_elements(x) && need[x] > 0;
-        if (streamed[0]) hs.A = A;
-        if (streamed[1]) hs.B = B;
-        if (streamed[2]) { hs.C_in = C; hs.C_out = C; }
-    }
-    const void* host_in[3] = {A, B, C};
-    for (int x = 0; x < 3; ++x) {
-        if (streamed[x] || (x == 2 && beta_zero)) continue;
-        const size_t bytes = p->schedule.initial_elements(x) * es;
-        if (bytes && cudaMemcpyAsync(p->owned[x], host_in[x], bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
-            return COSMA_B200_CUDA_ERROR;
-    }
-    bool needs_comm = false;
-    for (const auto& op : p->schedule.ops()) needs_comm |= op.kind != cosma::OpKind::GEMM;
-    if (needs_comm && p->ring_comms.empty()) {
-        set_last_error("plan was created without a communicator (plan-only); cannot execute collectives");
-        return COSMA_B200_INVALID_ARG;
-    }
-    const bool any = streamed[0] || streamed[1] || streamed[2];
-    int rc = cosma_b200::plan_run(*p, alpha, beta, p->owned[0], p->owned[1], p->owned[2], st, any ? &hs : nullptr);
-    if (rc != COSMA_B200_OK) return rc;
-    const size_t cbytes = p->schedule.initial_elements(2) * es;
-    if (!streamed[2] && cbytes && cudaMemcpyAsync(C, p->owned[2], cbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
-    return COSMA_B200_OK;
+            if (!p->owned[x]) {
+                const size_t bytes = std::max<size_t>(p->schedule.arena_elements(x), 1) * es;
+                if (cudaMalloc(reinterpret_cast<void**>(&p->owned[x]), bytes) != cudaSuccess) {
+                    set_last_error("cudaMalloc of a plan arena failed");
+                    return COSMA_B200_OUT_OF_MEMORY;
+                }
+            }
+        const bool beta_zero = beta[0] == 0.0 && (p->elem_reals == 1 || beta[1] == 0.0);
+        // A schedule with ONE base-case GEMM that reads a local matrix as the caller holds it (no allgather of that matrix
+        // before it) / leaves local C as the caller wants it (no reduce after it) streams that matrix over PCIe under the
+        // kernel instead of copying it up front (host_gemm.cu): P = 1, and the un-gathered operands of P > 1 strategies
+        // (pk2 at P = 2: A and B; pn2,pk2 at P = 4: B; pk8 of the large-K config: A and B).
+        const cosma::ScheduleOp* gemm_op = nullptr;
+        int n_gemm = 0;
+        bool gathered[3] = {false, false, false};
+        for (const auto& op : p->schedule.ops()) {
+            if (op.kind == cosma::OpKind::GEMM) { gemm_op = &op; ++n_gemm; }
+            else gathered[op.matrix] = true;
+        }
+        cosma_b200::HostOperands hs;
+        bool streamed[3] = {false, false, false};
+        if (n_gemm == 1) {
+            const auto& g = *gemm_op;
+            const int64_t need[3] = {int64_t(g.m) * g.k, int64_t(g.k) * g.n, int64_t(g.m) * g.n};
+            const int64_t off[3] = {g.a_off, g.b_off, g.c_off};
+            for (int x = 0; x < 3; ++x)
+                streamed[x] = !gathered[x] && off[x] == 0 && need[x] == p->schedule.initial_elements(x) && need[x] > 0;
+            if (streamed[0]) hs.A = A;
+            if (streamed[1]) hs.B = B;
+            if (streamed[2]) { hs.C_in = C; hs.C_out = C; }
+        }
+        const void* host_in[3] = {A, B, C};
+        for (int x = 0; x < 3; ++x) {
+            if (streamed[x] || (x == 2 && beta_zero)) continue;
+            const size_t bytes = p->schedule.initial_elements(x) * es;
+            if (bytes && cudaMemcpyAsync(p->owned[x], host_in[x], bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                return COSMA_B200_CUDA_ERROR;
+        }
+        bool needs_comm = false;
+        for (const auto& op : p->schedule.ops()) needs_comm |= op.kind != cosma::OpKind::GEMM;
+        if (needs_comm && p->ring_comms.empty()) {
+            set_last_error("plan was created without a communicator (plan-only); cannot execute collectives");
+            return COSMA_B200_INVALID_ARG;
+        }
+        const bool any = streamed[0] || streamed[1] || streamed[2];
+        int rc = cosma_b200::plan_run(*p, alpha, beta, p->owned[0], p->owned[1], p->owned[2], st, any ? &hs : nullptr);
+        if (rc != COSMA_B200_OK) return rc;
+        const size_t cbytes = p->schedule.initial_elements(2) * es;
+        if (!streamed[2] && cbytes && cudaMemcpyAsync(C, p->owned[2], cbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+        return COSMA_B200_OK;
+    });
 }
 
 int cosma_b200_plan_last_launches(void* plan) { return static_cast<Plan*>(plan)->last_launches; }
@@ -459,47 +487,51 @@ int cosma_b200_plan_time_gemms(void* plan, int enable) {
 }
 /* after a synchronised run with timing enabled: per-GEMM device milliseconds */
 int cosma_b200_plan_gemm_times(void* plan, float* out, int cap, int* n) {
-    Plan* p = static_cast<Plan*>(plan);
-    const auto& ops = p->schedule.ops();
-    int cnt = 0;
-    for (const auto& op : ops) cnt += op.kind == cosma::OpKind::GEMM;
-    *n = cnt;
-    if (!p->time_gemms || p->ev.size() < 2 * ops.size()) return COSMA_B200_INVALID_ARG;
-    int g = 0;
-    for (size_t i = 0; i < ops.size(); ++i) {
-        if (ops[i].kind != cosma::OpKind::GEMM) continue;
-        if (g < cap && cudaEventElapsedTime(&out[g], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
-        ++g;
-    }
-    return COSMA_B200_OK;
+    return guarded("cosma_b200_plan_gemm_times", [&]() -> int {
+        Plan* p = static_cast<Plan*>(plan);
+        const auto& ops = p->schedule.ops();
+        int cnt = 0;
+        for (const auto& op : ops) cnt += op.kind == cosma::OpKind::GEMM;
+        *n = cnt;
+        if (!p->time_gemms || p->ev.size() < 2 * ops.size()) return COSMA_B200_INVALID_ARG;
+        int g = 0;
+        for (size_t i = 0; i < ops.size(); ++i) {
+            if (ops[i].kind != cosma::OpKind::GEMM) continue;
+            if (g < cap && cudaEventElapsedTime(&out[g], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+            ++g;
+        }
+        return COSMA_B200_OK;
+    });
 }
 
 /* after a synchronised run with timing enabled: for every op of the schedule its kind (0 GEMM, 1 allgather, 2 reduce), device
  * milliseconds, and for collectives the bytes this rank puts on / takes off the wire: (d-1)/d of the gathered (allgather) or
  * reduced (reduce-scatter) buffer, d = ring size -- the "bus bandwidth" convention of SURVEY 8d. */
 int cosma_b200_plan_op_times(void* plan, int* kinds, float* ms, int64_t* wire_bytes, int cap, int* n) {
-    Plan* p = static_cast<Plan*>(plan);
-    if (!p || !n) return COSMA_B200_INVALID_ARG;
-    const auto& ops = p->schedule.ops();
-    *n = static_cast<int>(ops.size());
-    if (!p->time_gemms || p->ev.size() < 2 * ops.size()) return COSMA_B200_INVALID_ARG;
-    for (size_t i = 0; i < ops.size() && static_cast<int>(i) < cap; ++i) {
-        const auto& op = ops[i];
-        if (kinds) kinds[i] = op.kind == cosma::OpKind::GEMM ? 0 : (op.kind == cosma::OpKind::ALLGATHER ? 1 : 2);
-        if (ms && cudaEventElapsedTime(&ms[i], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
-        if (wire_bytes) {
-            int64_t total = 0, mine = 0;
-            if (op.kind != cosma::OpKind::GEMM) {
-                for (size_t g = 0; g < op.piece.size(); ++g)
-                    for (auto v : op.piece[g]) {
-                        total += v;
-                        if (static_cast<int>(g) == op.my_pos) mine += v;
-                    }
+    return guarded("cosma_b200_plan_op_times", [&]() -> int {
+        Plan* p = static_cast<Plan*>(plan);
+        if (!p || !n) return COSMA_B200_INVALID_ARG;
+        const auto& ops = p->schedule.ops();
+        *n = static_cast<int>(ops.size());
+        if (!p->time_gemms || p->ev.size() < 2 * ops.size()) return COSMA_B200_INVALID_ARG;
+        for (size_t i = 0; i < ops.size() && static_cast<int>(i) < cap; ++i) {
+            const auto& op = ops[i];
+            if (kinds) kinds[i] = op.kind == cosma::OpKind::GEMM ? 0 : (op.kind == cosma::OpKind::ALLGATHER ? 1 : 2);
+            if (ms && cudaEventElapsedTime(&ms[i], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+            if (wire_bytes) {
+                int64_t total = 0, mine = 0;
+                if (op.kind != cosma::OpKind::GEMM) {
+                    for (size_t g = 0; g < op.piece.size(); ++g)
+                        for (auto v : op.piece[g]) {
+                            total += v;
+                            if (static_cast<int>(g) == op.my_pos) mine += v;
+                        }
+                }
+                wire_bytes[i] = (total - mine) * p->elem_bytes();
             }
-            wire_bytes[i] = (total - mine) * p->elem_bytes();
         }
-    }
-    return COSMA_B200_OK;
+        return COSMA_B200_OK;
+    });
 }
 
 }  // extern "C"

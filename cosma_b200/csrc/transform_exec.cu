@@ -138,6 +138,7 @@ costa::erased_layout layout_from_c(const cosma_b200_layout& l, char ordering, in
 using cosma_b200::Comm;
 using cosma_b200::TransformPlan;
 using cosma_b200::set_last_error;
+using cosma_b200::guarded;
 
 extern "C" {
 
@@ -176,8 +177,10 @@ int cosma_b200_transform_plan_create(void* comm, int rank, int nranks, char dtyp
 }
 
 int cosma_b200_transform_run(void* plan, void* stream) {
-    if (!plan) return COSMA_B200_INVALID_ARG;
-    return cosma_b200::transform_plan_run(*static_cast<TransformPlan*>(plan), static_cast<cudaStream_t>(stream));
+    return guarded("cosma_b200_transform_run", [&]() -> int {
+        if (!plan) return COSMA_B200_INVALID_ARG;
+        return cosma_b200::transform_plan_run(*static_cast<TransformPlan*>(plan), static_cast<cudaStream_t>(stream));
+    });
 }
 
 int cosma_b200_transform_plan_destroy(void* plan) {
@@ -193,32 +196,36 @@ int cosma_b200_transform_plan_destroy(void* plan) {
 //     transpose, conjugate, transform, peer
 //   (pack: dst is a byte offset into the send buffer; unpack: src is a byte offset into the receive buffer)
 int cosma_b200_transform_plan_export(void* plan, int64_t* buf, int64_t cap, int64_t* len) {
-    if (!plan || !len) return COSMA_B200_INVALID_ARG;
-    const auto& h = static_cast<TransformPlan*>(plan)->host;
-    std::vector<int64_t> v = {h.n_ranks, h.elem_bytes, h.total_send, h.total_recv, static_cast<int64_t>(h.pack.size()),
-                              static_cast<int64_t>(h.local.size()), static_cast<int64_t>(h.unpack.size())};
-    for (const auto* arr : {&h.send_off, &h.send_bytes, &h.recv_off, &h.recv_bytes}) v.insert(v.end(), arr->begin(), arr->end());
-    int kind = 0;
-    for (const auto* list : {&h.pack, &h.local, &h.unpack}) {
-        for (const auto& p : *list) {
-            const int64_t rec[13] = {kind, reinterpret_cast<int64_t>(p.src), reinterpret_cast<int64_t>(p.dst), p.src_ld, p.dst_ld, p.n_rows,
-                                     p.n_cols, p.src_ordering, p.dst_ordering, p.transpose, p.conjugate, p.transform, p.peer};
-            v.insert(v.end(), rec, rec + 13);
+    return guarded("cosma_b200_transform_plan_export", [&]() -> int {
+        if (!plan || !len) return COSMA_B200_INVALID_ARG;
+        const auto& h = static_cast<TransformPlan*>(plan)->host;
+        std::vector<int64_t> v = {h.n_ranks, h.elem_bytes, h.total_send, h.total_recv, static_cast<int64_t>(h.pack.size()),
+                                  static_cast<int64_t>(h.local.size()), static_cast<int64_t>(h.unpack.size())};
+        for (const auto* arr : {&h.send_off, &h.send_bytes, &h.recv_off, &h.recv_bytes}) v.insert(v.end(), arr->begin(), arr->end());
+        int kind = 0;
+        for (const auto* list : {&h.pack, &h.local, &h.unpack}) {
+            for (const auto& p : *list) {
+                const int64_t rec[13] = {kind, reinterpret_cast<int64_t>(p.src), reinterpret_cast<int64_t>(p.dst), p.src_ld, p.dst_ld, p.n_rows,
+                                         p.n_cols, p.src_ordering, p.dst_ordering, p.transpose, p.conjugate, p.transform, p.peer};
+                v.insert(v.end(), rec, rec + 13);
+            }
+            ++kind;
         }
-        ++kind;
-    }
-    *len = static_cast<int64_t>(v.size());
-    if (buf && cap >= *len) std::memcpy(buf, v.data(), v.size() * sizeof(int64_t));
-    return COSMA_B200_OK;
+        *len = static_cast<int64_t>(v.size());
+        if (buf && cap >= *len) std::memcpy(buf, v.data(), v.size() * sizeof(int64_t));
+        return COSMA_B200_OK;
+    });
 }
 
 int cosma_b200_transform_plan_stats(void* plan, int64_t* local_elements, int64_t* remote_elements, int* launches) {
-    if (!plan) return COSMA_B200_INVALID_ARG;
-    const auto* tp = static_cast<TransformPlan*>(plan);
-    if (local_elements) *local_elements = tp->host.local_elements;
-    if (remote_elements) *remote_elements = tp->host.remote_elements;
-    if (launches) *launches = tp->last_launches;
-    return COSMA_B200_OK;
+    return guarded("cosma_b200_transform_plan_stats", [&]() -> int {
+        if (!plan) return COSMA_B200_INVALID_ARG;
+        const auto* tp = static_cast<TransformPlan*>(plan);
+        if (local_elements) *local_elements = tp->host.local_elements;
+        if (remote_elements) *remote_elements = tp->host.remote_elements;
+        if (launches) *launches = tp->last_launches;
+        return COSMA_B200_OK;
+    });
 }
 
 int cosma_b200_relayout_batch(void* stream, char dtype, int n, const cosma_b200_piece* pieces) {

@@ -38,3 +38,32 @@ def test_no_oracle_in_product():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "liboracle" in txt or "libcosma_ref" in txt:
                     bad.append(os.path.join(root, f))
     assert not bad, bad
+
+
+def test_plan_accessors_reject_bad_arguments_instead_of_throwing(lib):
+    """No C++ exception crosses the C ABI: null handles, matrix indices outside 0..2 and ranks the strategy does not use come back as
+    status codes (planning only: no GPU needed)."""
+    import ctypes
+    from cosma_b200.distributed import MultiplyPlan
+    pl = MultiplyPlan(None, 64, 48, 32, "pm2", "d", rank=0, nranks=2, allocate=False)
+    L, h = pl.lib, pl.handle
+    n = ctypes.c_int(-7)
+    assert L.cosma_b200_plan_local_blocks(h, 0, 2, None, 0, ctypes.byref(n)) == 0 and n.value == 0        # not a rank of the strategy: owns nothing
+    assert L.cosma_b200_plan_local_blocks(h, 0, 99, None, 0, ctypes.byref(n)) == 0 and n.value == 0
+    assert L.cosma_b200_plan_local_blocks(h, 0, 1, None, 0, ctypes.byref(n)) == 0 and n.value >= 1
+    assert L.cosma_b200_plan_local_blocks(h, 3, 0, None, 0, ctypes.byref(n)) == 1                         # COSMA_B200_INVALID_ARG
+    assert L.cosma_b200_plan_local_blocks(None, 0, 0, None, 0, ctypes.byref(n)) == 1
+    assert L.cosma_b200_plan_local_blocks(h, 0, 0, None, 0, None) == 1
+    L.cosma_b200_plan_arena_elements.restype = ctypes.c_int64
+    assert L.cosma_b200_plan_arena_elements(h, 5) == -1 and L.cosma_b200_plan_arena_elements(None, 0) == -1
+    assert L.cosma_b200_plan_arena_elements(h, 2) > 0
+    buf = ctypes.create_string_buffer(2)
+    assert L.cosma_b200_plan_strategy(h, buf, 2, None) == 1                                               # buffer too small
+    assert L.cosma_b200_plan_strategy(None, buf, 2, None) == 1
+    ln = ctypes.c_int64(0)
+    assert L.cosma_b200_plan_export(None, None, 0, ctypes.byref(ln)) == 1
+    assert L.cosma_b200_plan_export(h, None, 0, ctypes.byref(ln)) == 0 and ln.value > 0
+    a = (ctypes.c_double * 2)(1.0, 0.0)
+    assert L.cosma_b200_multiply(None, a, a, None, None, None, None) == 1
+    assert L.cosma_b200_transform_run(None, None) != 0
+    pl.destroy()
