@@ -81,3 +81,29 @@ def adapt_strategy(m, n, k, P, desca, ia, ja, descb, ib, jb, descc, ic, jc, tran
                                        ctypes.c_char(transb.encode()), nprow, npcol, ctypes.c_char(order.encode()), out, 512)
     _lib.check(st, "cosma_b200_adapt_strategy")
     return out.value.decode()
+
+
+def comm_volume(grid_a, grid_b, trans, n_ranks):
+    """cosma_b200_comm_volume: elements exchanged between every pair of ranks when a matrix moves from grid_a (transposed first when trans
+    != 'N') to grid_b. grid = (rowsplit, colsplit, owners[rows][cols]). -> n_ranks x n_ranks nested list, upper triangle, [u][u] stays."""
+    lib = _lib.load()
+
+    def pack(g):
+        rs, cs, ow = g
+        flat = [int(o) for row in ow for o in row]
+        return len(rs) - 1, len(cs) - 1, (ctypes.c_int * len(rs))(*rs), (ctypes.c_int * len(cs))(*cs), (ctypes.c_int * max(len(flat), 1))(*flat)
+    a, b = pack(grid_a), pack(grid_b)
+    vol = (ctypes.c_longlong * (n_ranks * n_ranks))()
+    st = lib.cosma_b200_comm_volume(a[0], a[1], a[2], a[3], a[4], b[0], b[1], b[2], b[3], b[4], ctypes.c_char(trans.encode()), n_ranks, vol)
+    _lib.check(st, "cosma_b200_comm_volume")
+    return [[vol[u * n_ranks + v] for v in range(n_ranks)] for u in range(n_ranks)]
+
+
+def optimal_reordering(volume):
+    """cosma_b200_optimal_reordering on a comm_volume() result (or a sum of several). -> (permutation, reordered)."""
+    lib = _lib.load()
+    n = len(volume)
+    flat = (ctypes.c_longlong * (n * n))(*[int(volume[u][v]) for u in range(n) for v in range(n)])
+    perm, flag = (ctypes.c_int * n)(), ctypes.c_int(0)
+    _lib.check(lib.cosma_b200_optimal_reordering(n, flat, perm, ctypes.byref(flag)), "cosma_b200_optimal_reordering")
+    return list(perm), bool(flag.value)

@@ -1,11 +1,13 @@
 """cosma_statistics for cosma_b200: what a multiply of (m, n, k) on P ranks will do, without running it (no GPU needed).
 
-    python -m cosma_b200.statistics -m 32768 -n 32768 -k 32768 -P 8 [-s pm2,pn2,pk2] [-t double]
+    python -m cosma_b200.statistics -m 32768 -n 32768 -k 32768 -P 8 [-s pm2,pn2,pk2] [-t double] [--layout]
+    python -m cosma_b200.statistics -m 16384 -n 16384 -k 16384 -P 8 -t zdouble --pxgemm --block_a 256,256 -p 2,4 --transpose CN
 
 Prints the strategy, the per-rank device arenas of the compiled schedule, the collectives with the bytes each rank puts on the
 wire ((d-1)/d of the gathered / reduced buffer, ring size d) and the local GEMMs, plus a time estimate from this pool's measured
 rates. The reference's tool of the same name (miniapp/cosma_statistics.cpp) walks its recursion with a counting communicator; here
-the compiled op list already is that walk."""
+the compiled op list already is that walk. --pxgemm adds what the relayouts of a p?gemm call on block-cyclic matrices move, for the
+communication-optimal and the grid-adapted strategy, and what rank relabelling would keep in place (COSTA's comm_volume miniapp)."""
 import argparse
 import sys
 
@@ -71,6 +73,35 @@ def layouts(m, n, k, P, steps=""):
     return full, out
 
 
+def pxgemm_relayout(m, n, k, P, nprow, npcol, order, trans, blocks, steps=""):
+    """What the relayouts of a p?gemm call move: for op(A), op(B) (block-cyclic -> COSMA's native layout of `steps`) and C (native ->
+    block-cyclic) the elements that stay on their rank and those that cross, plus what rank relabelling (costa::optimal_reordering on
+    the summed volume graph, reference cosma_pxgemm.cpp:255-271) would keep in place. blocks: ((mb, nb) of A, of B, of C)."""
+    from . import costa, planning
+    ta, tb = trans[0].upper(), trans[1].upper()
+    shapes = {"A": (m, k) if ta == "N" else (k, m), "B": (k, n) if tb == "N" else (n, k), "C": (m, n)}
+    full, native = layouts(m, n, k, P, steps)
+    total = [[0] * P for _ in range(P)]
+    rows = []
+    for label, blk, tr in (("A", blocks[0], ta), ("B", blocks[1], tb), ("C", blocks[2], "N")):
+        r, c = shapes[label]
+        rs, cs, ow, _ = costa.scalapack_grid(max(r, 1), r, c, 1, 1, r, c, blk[0], blk[1], nprow, npcol, order, 0, 0, "C", 0)
+        user = (list(rs), list(cs), [[int(ow[i][j]) for j in range(len(cs) - 1)] for i in range(len(rs) - 1)])
+        nat = native[label]
+        nat = (nat[0], nat[1], [[max(o, 0) for o in row] for row in nat[2]])
+        vol = planning.comm_volume(user, nat, tr, P) if label != "C" else planning.comm_volume(nat, user, "N", P)
+        stay = sum(vol[u][u] for u in range(P))
+        rows.append((label, r * c, stay, r * c - stay))
+        for u in range(P):
+            for v in range(P):
+                total[u][v] += vol[u][v]
+    perm, reordered = planning.optimal_reordering(total)
+    kept = sum(total[u][u] for u in range(P))
+    kept_relabelled = sum(total[min(u, perm[u])][max(u, perm[u])] for u in range(P) if perm[u] >= u)
+    return {"strategy": full, "matrices": rows, "stay": kept, "stay_relabelled": kept_relabelled if reordered else kept, "permutation": perm,
+            "reordered": reordered, "elements": sum(x[1] for x in rows)}
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="cosma_b200.statistics")
     ap.add_argument("-m", type=int, required=True)
@@ -80,6 +111,13 @@ def main(argv=None):
     ap.add_argument("-s", "--steps", default="")
     ap.add_argument("-t", "--type", default="double", choices=sorted(BYTES))
     ap.add_argument("--layout", action="store_true", help="also print the native layout grids of A, B, C (layout_miniapp)")
+    ap.add_argument("--pxgemm", action="store_true", help="also print what the relayouts of a p?gemm call on block-cyclic matrices move")
+    ap.add_argument("--block_a", default="128,128")
+    ap.add_argument("--block_b", default="128,128")
+    ap.add_argument("--block_c", default="128,128")
+    ap.add_argument("-p", "--p_grid", default="", help="nprow,npcol (default: the most square grid of P)")
+    ap.add_argument("--order", default="R", choices=["R", "C"])
+    ap.add_argument("--transpose", default="NN")
     a = ap.parse_args(argv)
     ranks = None if a.P <= 64 else [0, 1, a.P // 2, a.P - 1]
     d = describe(a.m, a.n, a.k, a.P, a.steps, a.type, ranks)
@@ -102,6 +140,32 @@ def main(argv=None):
                 print("             owners " + " ".join("%3d" % o for o in row[:32]) + (" ..." if len(row) > 32 else ""))
             if len(owners) > 16:
                 print("             ... %d more block rows" % (len(owners) - 16))
+    if a.pxgemm:
+        from . import planning
+        pair = lambda t: tuple(int(x) for x in t.split(","))
+        if a.p_grid:
+            nprow, npcol = pair(a.p_grid)
+        else:
+            nprow = max(d for d in range(1, int(a.P ** 0.5) + 1) if a.P % d == 0)
+            npcol = a.P // nprow
+        blocks = (pair(a.block_a), pair(a.block_b), pair(a.block_c))
+        ta, tb = a.transpose[0].upper(), a.transpose[1].upper()
+        shape = lambda r, c, t: (r, c) if t == "N" else (c, r)
+        desc = lambda rc, blk: [1, 0, rc[0], rc[1], blk[0], blk[1], 0, 0, max(rc[0], 1)]
+        variants = [("communication-optimal strategy", a.steps)]
+        prefix = planning.adapt_strategy(a.m, a.n, a.k, a.P, desc(shape(a.m, a.k, ta), blocks[0]), 1, 1, desc(shape(a.k, a.n, tb), blocks[1]), 1, 1,
+                                         desc((a.m, a.n), blocks[2]), 1, 1, ta, tb, nprow, npcol, a.order)
+        if prefix and not a.steps:
+            variants.append(("COSMA_ADAPT_STRATEGY=ON", planning.strategy(a.m, a.n, a.k, a.P, 0, prefix)[0]))
+        print("p?gemm    : grid %d x %d (%s), op = %s, blocks A %s B %s C %s" % (nprow, npcol, a.order, a.transpose.upper(), blocks[0], blocks[1], blocks[2]))
+        for name, steps in variants:
+            r = pxgemm_relayout(a.m, a.n, a.k, a.P, nprow, npcol, a.order, a.transpose, blocks, steps)
+            print("  %s [%s]" % (name, r["strategy"] if len(r["strategy"]) < 60 else r["strategy"][:57] + "..."))
+            for label, elems, stay, cross in r["matrices"]:
+                print("    relayout of %s: %5.1f %% of %d elements change rank" % (label, 100.0 * cross / max(elems, 1), elems))
+            print("    in place: %.1f %%; with rank relabelling (COSMA_B200_REORDER_RANKS=ON): %.1f %%%s" %
+                  (100.0 * r["stay"] / max(r["elements"], 1), 100.0 * r["stay_relabelled"] / max(r["elements"], 1),
+                   "" if r["reordered"] else " (nothing to gain)"))
     return 0
 
 

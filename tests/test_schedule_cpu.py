@@ -74,6 +74,28 @@ def test_statistics_tool(lib, capsys):
     assert "strategy  : pk8" in out and "reduce     C  ring of 8" in out
 
 
+def test_statistics_pxgemm_relayout(lib, capsys):
+    """--pxgemm: relayout volumes of BASELINE configs[4] (pzgemm 16384^3, 2 x 4 grid, 256^2 blocks, A conjugate-transposed). The adapted
+    strategy leaves A where it is; a COSMA layout handed in under reversed rank labels is found again by the relabelling."""
+    from cosma_b200 import planning, statistics
+    r = statistics.pxgemm_relayout(16384, 16384, 16384, 8, 2, 4, "R", "CN", ((256, 256),) * 3)
+    assert r["strategy"] == "pm2,pn2,pk2" and r["elements"] == 3 * 16384 ** 2
+    assert [x[0] for x in r["matrices"]] == ["A", "B", "C"] and all(x[2] + x[3] == 16384 ** 2 for x in r["matrices"])
+    assert not r["reordered"] and r["stay_relabelled"] == r["stay"]            # all rank pairs exchange the same volume
+    ad = statistics.pxgemm_relayout(16384, 16384, 16384, 8, 2, 4, "R", "CN", ((256, 256),) * 3, "sk32,sm16,pk2,pm4")
+    assert ad["matrices"][0][3] == 0 and ad["stay"] > r["stay"]                # A does not move
+    # native layout against itself with the rank labels reversed: nothing is in place, relabelling recovers everything
+    _, nat = statistics.layouts(4096, 4096, 4096, 8)
+    rs, cs, ow = nat["A"]
+    rev = (rs, cs, [[7 - o for o in row] for row in ow])
+    vol = planning.comm_volume(rev, (rs, cs, ow), "N", 8)
+    perm, flag = planning.optimal_reordering(vol)
+    assert flag and sum(vol[u][u] for u in range(8)) == 0 and perm == [7 - u for u in range(8)]
+    assert statistics.main(["-m", "2048", "-n", "2048", "-k", "2048", "-P", "4", "--pxgemm", "--block_a", "64,64", "--transpose", "TN"]) == 0
+    out = capsys.readouterr().out
+    assert "p?gemm    : grid 2 x 2 (R), op = TN" in out and "relayout of C" in out and "in place:" in out
+
+
 def test_over_divided_dimension_is_refused(lib):
     """m = 2 cut into 3 sequential parts: the reference's Strategy accepts it and its multiply then returns a wrong product
     (Interval::subinterval returns the whole interval, interval.cpp:84-98). The plan refuses with a clear message instead."""
