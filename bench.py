@@ -224,7 +224,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = None
     if world > 1:
+        # several ranks share the host: keep each rank (and the pinned buffers it allocates) on the NUMA node of its GPU
+        try:
+            from cosma_b200 import affinity as _aff
+            affinity = _aff.bind_to_gpu(local_rank)
+        except Exception:
+            affinity = None
         dist.init_process_group("nccl", device_id=dev)
     from cosma_b200 import _lib, gemm
     lib = _lib.load()  # raises if the CUDA library is missing: there is no CPU fallback
@@ -349,6 +356,8 @@ def main():
                            "l2": "inputs larger than L2 (A+B+C = %.1f GB per job vs 126 MB L2)" % (8e-9 * (m * k + k * n + m * n)),
                            "fp64_peak_per_gpu_tflops": peak, "frac_of_fp64_peak": value / (peak * world)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if affinity is not None:
+            line["config"]["host_affinity_rank0"] = affinity
         if collectives is not None:
             line["collectives"] = collectives  # rank 0's allgather / reduce-scatter device time and bus bandwidth in the last timed step
         print(json.dumps(line))

@@ -32,3 +32,16 @@ def test_other_ranks_of_the_reference_arm_do_nothing(ref):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                          capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_host_affinity_helper_is_best_effort():
+    """cosma_b200.affinity: cpulist parsing; without a GPU / sysfs entry nothing is bound and nothing raises."""
+    import os
+    from cosma_b200 import affinity
+    assert affinity._cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and affinity._cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = affinity.bind_to_gpu(0)
+    assert set(info) == {"numa_node", "cpus", "bound"}
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
