@@ -1,6 +1,12 @@
 #include <cosma/b200_runtime.hpp>
 #include <cosma/environment_variables.hpp>
 
+#include <sched.h>
+
+#include <fstream>
+#include <sstream>
+#include <string>
+
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -38,7 +44,38 @@ void select_device() {
         const char* lr = std::getenv("LOCAL_RANK");
         const int local = lr && *lr ? std::atoi(lr) : 0;
         check(cosma_b200_set_device(local % n), "cosma_b200_set_device");
+        if (get_bool_env_var("COSMA_B200_BIND_NUMA", false)) bind_to_device_numa_node(local % n);
     });
+}
+
+// COSMA_B200_BIND_NUMA=ON: run on the CPUs local to the rank's GPU (sysfs local_cpulist of its PCI function), so that the page-locked
+// buffers of the memory pool (first touch) sit next to that GPU's PCIe root -- what `mpirun --bind-to` / numactl does for the
+// reference on multi-socket hosts. Best effort: anything missing leaves the affinity as it is.
+bool bind_to_device_numa_node(int device) {
+    char bdf[32] = {0};
+    if (cosma_b200_device_pci_bus_id(device, bdf, sizeof bdf) != COSMA_B200_OK) return false;
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist");
+    std::string list;
+    if (!f || !std::getline(f, list)) return false;
+    cpu_set_t allowed, target;
+    CPU_ZERO(&allowed);
+    CPU_ZERO(&target);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return false;
+    int in_target = 0, in_allowed = CPU_COUNT(&allowed);
+    std::stringstream parts(list);
+    std::string part;
+    while (std::getline(parts, part, ',')) {
+        if (part.empty()) continue;
+        const auto dash = part.find('-');
+        const int lo = std::atoi(part.substr(0, dash).c_str());
+        const int hi = dash == std::string::npos ? lo : std::atoi(part.substr(dash + 1).c_str());
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c)
+            if (c >= 0 && CPU_ISSET(c, &allowed) && !CPU_ISSET(c, &target)) { CPU_SET(c, &target); ++in_target; }
+    }
+    if (in_target == 0 || in_target == in_allowed) return false;
+    const bool ok = sched_setaffinity(0, sizeof target, &target) == 0;
+    if (ok) trace(("bound to the " + std::to_string(in_target) + " CPUs local to device " + bdf).c_str());
+    return ok;
 }
 
 namespace {

@@ -94,6 +94,14 @@ int cosma_b200_device_count(int* count) {
     return cuda_status(cudaGetDeviceCount(count), "cudaGetDeviceCount");
 }
 int cosma_b200_set_device(int device) { return cuda_status(cudaSetDevice(device), "cudaSetDevice"); }
+int cosma_b200_device_pci_bus_id(int device, char* out, int out_len) {
+    if (!out || out_len < 13) return COSMA_B200_INVALID_ARG;
+    const int st = cuda_status(cudaDeviceGetPCIBusId(out, out_len, device), "cudaDeviceGetPCIBusId");
+    if (st != COSMA_B200_OK) return st;
+    for (char* c = out; *c; ++c)
+        if (*c >= 'A' && *c <= 'Z') *c = static_cast<char>(*c - 'A' + 'a');
+    return COSMA_B200_OK;
+}
 int cosma_b200_stream_synchronize(void* stream) {
     return cuda_status(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
 }

@@ -30,6 +30,8 @@ template <typename T> inline void to_pair(const std::complex<T>& v, double out[2
 // One process drives one GPU: on first use selects device LOCAL_RANK % device_count (the reference does the same per
 // rank in its GPU context, libs/Tiled-MM/src/Tiled-MM/mm_handle.cpp). COSMA_B200_KEEP_DEVICE=ON leaves the current device.
 void select_device();
+// COSMA_B200_BIND_NUMA=ON (applied by select_device): restrict the process to the CPUs local to `device`; false when nothing was changed.
+bool bind_to_device_numa_node(int device);
 
 // The NCCL communicator of `comm` (all of its ranks), created collectively on first use -- rank 0 obtains the
 // ncclUniqueId and broadcasts it over `comm` as the reference does (src/cosma/gpu/nccl_utils.cpp:21-42) -- and cached by

@@ -333,6 +333,9 @@ COSMA_B200_API int cosma_b200_host_register(void* ptr, uint64_t bytes);
 COSMA_B200_API int cosma_b200_host_unregister(void* ptr);
 COSMA_B200_API int cosma_b200_device_count(int* count);
 COSMA_B200_API int cosma_b200_set_device(int device);
+/* "domain:bus:device.function" of a CUDA device, lower case, as under /sys/bus/pci/devices (cudaDeviceGetPCIBusId): what a host needs
+ * to place a rank on the NUMA node of its GPU (an MPI launcher's binding does this for the reference). */
+COSMA_B200_API int cosma_b200_device_pci_bus_id(int device, char* out, int out_len);
 /* Blocks until everything queued on `stream` (NULL: the default stream) has finished. */
 COSMA_B200_API int cosma_b200_stream_synchronize(void* stream);
 

@@ -308,6 +308,12 @@ const char* cosma_b200_last_error(void) { return g_err.c_str(); }
 
 int cosma_b200_device_count(int* count) { *count = 1; return COSMA_B200_OK; }
 int cosma_b200_set_device(int) { return COSMA_B200_OK; }
+int cosma_b200_device_pci_bus_id(int, char* out, int out_len) {  // MOCK_PCI_BDF: a PCI function that exists under /sys/bus/pci/devices
+    const char* v = std::getenv("MOCK_PCI_BDF");
+    if (!v || !out || static_cast<int>(std::strlen(v)) + 1 > out_len) return COSMA_B200_CUDA_ERROR;
+    std::strcpy(out, v);
+    return COSMA_B200_OK;
+}
 int cosma_b200_stream_synchronize(void*) { return COSMA_B200_OK; }
 int cosma_b200_host_alloc(void** ptr, uint64_t bytes) {
     *ptr = bytes ? std::malloc(bytes) : nullptr;

@@ -242,6 +242,17 @@ def test_cosma_miniapp_multirank_on_cpu(host_libs, np_, args):
     assert "COSMA TIMES [ms] =" in out and "Strategy" in out, out
 
 
+def test_numa_binding_switch_is_best_effort(host_libs):
+    """COSMA_B200_BIND_NUMA=ON: the runtime reads the local_cpulist of the device's PCI function and restricts the process to it when
+    that is a proper subset of its CPUs; here (one NUMA node, or no such sysfs entry) nothing changes and the run is unaffected."""
+    from cosma_b200.launch import launch
+    devs = sorted(os.listdir("/sys/bus/pci/devices")) if os.path.isdir("/sys/bus/pci/devices") else []
+    for bdf in ([devs[0]] if devs else []) + ["ffff:ff:1f.7"]:
+        code, outs = launch(2, [program("cosma_miniapp"), "-m", "96", "-n", "80", "-k", "64", "-r", "1"], timeout=120, capture=True,
+                            env_extra={"LD_PRELOAD": _mock(), "COSMA_B200_BIND_NUMA": "ON", "MOCK_PCI_BDF": bdf, "COSMA_B200_TRACE": "ON"})
+        assert code == 0 and "COSMA TIMES [ms] =" in outs[0], outs[0][-2000:]
+
+
 def test_pxgemm_miniapp_multirank_on_cpu(host_libs):
     out = _run_on_mock(6, [program("pxgemm_miniapp"), "-m", "200", "-n", "150", "-k", "100", "--block_a", "32,16", "--block_b", "8,8", "--block_c", "16,32",
                            "--transpose", "TN", "-p", "2,3", "-r", "2", "--type", "zdouble"])
