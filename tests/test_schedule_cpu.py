@@ -104,3 +104,68 @@ def test_over_divided_dimension_is_refused(lib):
         MultiplyPlan(None, 2, 14, 55, "sm3", "d", rank=0, nranks=1, allocate=False)
     pl = MultiplyPlan(None, 3, 14, 55, "sm3", "d", rank=0, nranks=1, allocate=False)  # exactly one row per part is fine
     pl.destroy()
+
+
+@pytest.mark.parametrize("P,steps,m,n,k,c", [(8, "pm2,pn2,pk2", 64, 96, 80, 4), (4, "pn2,pk2", 48, 64, 40, 2), (2, "pk2", 40, 36, 64, 3),
+                                             (8, "pk8", 32, 48, 128, 3), (8, "pm2,pn2,pk2", 60, 72, 56, 3), (4, "pm2,pk2", 36, 40, 44, 5)])
+def test_column_panels_of_the_local_buffers_are_independent_subproblems(lib, P, steps, m, n, k, c):
+    """The plan for end-to-end pipelining at N > 1: cut every rank's LOCAL C into c column chunks (contiguous in the
+    column-major local buffer) and its local B into the matching columns -- for every C column range [c0, c1) that lies inside the rank's
+    B columns (one per member of the k-ring that shares this B), the j-th c-th of it; each piece is contiguous in local B. Chunk j of all
+    ranks is then exactly the native layout of the smaller problem (m, n / c, k) under the same strategy (a product over a subset of the
+    columns), so c sub-plans, with A uploaded and gathered once, give the full product bit for bit while chunk j + 1 travels up and
+    chunk j - 1 travels down under the GEMM of chunk j. (Taking contiguous c-ths of local B instead is WRONG whenever C is divided
+    more finely than B, e.g. pn2,pk2: the values land on other ranks.)"""
+    import numpy as np
+    from cosma_b200.distributed import MultiplyPlan, fill_local_from_global
+    from schedule_sim import run_schedules
+    rng = np.random.default_rng(P * 1000 + n)
+    Ag, Bg = rng.integers(-5, 6, size=(m, k)).astype(np.float64), rng.integers(-5, 6, size=(k, n)).astype(np.float64)
+    Cg = rng.integers(-5, 6, size=(m, n)).astype(np.float64)
+    alpha, beta = 2.0, -1.0
+    full = [MultiplyPlan(None, m, n, k, steps, "d", rank=r, nranks=P, allocate=False) for r in range(P)]
+    sub = [MultiplyPlan(None, m, n // c, k, steps, "d", rank=r, nranks=P, allocate=False) for r in range(P)]
+    assert full[0].strategy == sub[0].strategy == steps
+    arenas = []
+    for pl in full:
+        bufs = [np.zeros(max(pl.arena_elements[x], 1)) for x in range(3)]
+        for x, (label, G) in enumerate((("A", Ag), ("B", Bg), ("C", Cg))):
+            fill_local_from_global(pl, label, bufs[x], G)
+        arenas.append(bufs)
+    locals_in = [[a[x][:pl.initial_elements[x]].copy() for x in range(3)] for a, pl in zip(arenas, full)]
+    run_schedules(full, arenas, alpha, beta)
+    want = [a[2][:pl.initial_elements[2]].copy() for a, pl in zip(arenas, full)]
+    blocks = {x: [full[r].local_blocks(x) for r in range(P)] for x in "BC"}
+    for r in range(P):
+        assert sub[r].initial_elements[0] == full[r].initial_elements[0]                      # A is shared by all chunks
+        assert sub[r].initial_elements[1] * c == full[r].initial_elements[1] and sub[r].initial_elements[2] * c == full[r].initial_elements[2]
+        assert len(blocks["B"][r]) == 1 and len(blocks["C"][r]) == 1                          # one column-major block each
+    c_ranges = sorted({(b[0][2], b[0][3] + 1) for b in blocks["C"]})
+    got = [np.empty_like(w) for w in want]
+    for j in range(c):
+        sa = []
+        for r in range(P):
+            bufs = [np.zeros(max(sub[r].arena_elements[x], 1)) for x in range(3)]
+            bufs[0][:sub[r].initial_elements[0]] = locals_in[r][0]
+            (r0, r1, b0, b1) = blocks["B"][r][0]
+            rows, pos = r1 - r0 + 1, 0
+            for (c0, c1) in c_ranges:                       # the C column ranges inside this rank's B columns, in order
+                if c0 < b0 or c1 > b1 + 1:
+                    continue
+                w = (c1 - c0) // c
+                assert w * c == c1 - c0
+                lo = (c0 - b0 + j * w) * rows               # contiguous piece of the column-major local B
+                bufs[1][pos:pos + w * rows] = locals_in[r][1][lo:lo + w * rows]
+                pos += w * rows
+            assert pos == sub[r].initial_elements[1]
+            nc = sub[r].initial_elements[2]
+            bufs[2][:nc] = locals_in[r][2][j * nc:(j + 1) * nc]
+            sa.append(bufs)
+        run_schedules(sub, sa, alpha, beta)
+        for r in range(P):
+            nc = sub[r].initial_elements[2]
+            got[r][j * nc:(j + 1) * nc] = sa[r][2][:nc]
+    for r in range(P):
+        assert np.array_equal(got[r], want[r]), r
+    for pl in full + sub:
+        pl.destroy()
