@@ -44,7 +44,26 @@ struct Plan {
     bool time_gemms = false;
     // library-owned device arenas for the host-pointer entry point (allocated on first use)
     char* owned[3] = {nullptr, nullptr, nullptr};
+    // column-panel pipelining of the host-pointer entry point (COSMA_B200_HOST_PANELS, multiply_exec.cu): the plan of one panel
+    // (m, n / c, k, same strategy, this plan's ring communicators borrowed), two B / C arena sets, copy streams and events
+    bool borrowed_comms = false;
+    Plan* panel_plan = nullptr;
+    int panel_count = 0;
+    char* panel_arena[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [set][0 = B, 1 = C]
+    cudaStream_t panel_in = nullptr, panel_out = nullptr;
+    std::vector<cudaEvent_t> panel_ev;
 };
+
+// One piece of a rank's local B that belongs to column panel j: `len` elements from src_off of the local buffer go to dst_off of the
+// panel's local B.
+struct PanelPiece {
+    std::int64_t src_off, len, dst_off;
+};
+// Column panel j of c of this rank's local matrices: local C columns [j, j+1) * (width / c) -- contiguous -- and,
+// for every C column range of the ranks that lies inside this rank's B columns, the j-th c-th of it. False when the layout does not
+// allow it (several blocks per rank, widths not divisible by c, C ranges that do not tile the B columns).
+bool host_panel_pieces(const cosma::Schedule& schedule, int rank, int c, int j, std::vector<PanelPiece>& b_pieces, std::int64_t& c_off,
+                       std::int64_t& c_len);
 
 // host copies of the local matrices for the one GEMM of a schedule that can stream them (multiply_exec.cu)
 struct HostOperands {

@@ -188,6 +188,44 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
     return COSMA_B200_OK;
 }
 
+bool host_panel_pieces(const cosma::Schedule& schedule, int rank, int c, int j, std::vector<PanelPiece>& b_pieces, std::int64_t& c_off,
+                       std::int64_t& c_len) {
+    b_pieces.clear();
+    const int P = static_cast<int>(schedule.strategy().P);
+    if (c < 1 || j < 0 || j >= c || rank < 0 || rank >= P) return false;
+    const auto& myB = schedule.mapper(1).initial_layout(rank);
+    const auto& myC = schedule.mapper(2).initial_layout(rank);
+    if (myB.size() != 1 || myC.size() != 1) return false;
+    std::vector<std::pair<int, int>> ranges;  // distinct [first, last] column ranges of the ranks' C blocks
+    for (int q = 0; q < P; ++q) {
+        const auto& blocks = schedule.mapper(2).initial_layout(q);
+        if (blocks.size() != 1) return false;
+        ranges.emplace_back(blocks[0].cols.first(), blocks[0].cols.last());
+    }
+    std::sort(ranges.begin(), ranges.end());
+    ranges.erase(std::unique(ranges.begin(), ranges.end()), ranges.end());
+    const std::int64_t b0 = myB[0].cols.first(), b1 = myB[0].cols.last(), rows = myB[0].rows.length();
+    std::int64_t pos = 0, covered = 0;
+    for (const auto& rg : ranges) {
+        if (rg.first < b0 || rg.second > b1) {
+            if (rg.second >= b0 && rg.first <= b1) return false;  // straddles the edge of this rank's B columns
+            continue;
+        }
+        const std::int64_t width = rg.second - rg.first + 1;
+        if (width % c != 0) return false;
+        const std::int64_t w = width / c;
+        b_pieces.push_back(PanelPiece{(rg.first - b0 + j * w) * rows, w * rows, pos});
+        pos += w * rows;
+        covered += width;
+    }
+    if (covered != b1 - b0 + 1) return false;
+    const std::int64_t cw = myC[0].cols.length();
+    if (cw % c != 0) return false;
+    c_len = (cw / c) * static_cast<std::int64_t>(myC[0].rows.length());
+    c_off = j * c_len;
+    return true;
+}
+
 }  // namespace cosma_b200
 
 using cosma_b200::Comm;
@@ -395,6 +433,23 @@ int cosma_b200_plan_local_blocks(void* plan, int matrix, int rank, int* out, int
                 out[4 * i + 2] = blocks[i].cols.first(); out[4 * i + 3] = blocks[i].cols.last();
             }
         return static_cast<int>(COSMA_B200_OK);
+    });
+}
+
+/* Planning only: column panel j of c of this plan's rank (exec_internal.h host_panel_pieces). pieces: (src_off, len, dst_off) triples of
+ * local B; the panel of local C is c_len elements from c_off. *eligible = 0 when the layout cannot be cut this way. */
+int cosma_b200_plan_host_panel(void* plan, int c, int j, int64_t* pieces, int cap, int* n_pieces, int64_t* c_off, int64_t* c_len, int* eligible) {
+    if (!plan || !n_pieces || !c_off || !c_len || !eligible) return COSMA_B200_INVALID_ARG;
+    return guarded("cosma_b200_plan_host_panel", [&]() -> int {
+        Plan* p = static_cast<Plan*>(plan);
+        std::vector<cosma_b200::PanelPiece> v;
+        *n_pieces = 0; *c_off = 0; *c_len = 0;
+        *eligible = !p->schedule.idle() && cosma_b200::host_panel_pieces(p->schedule, p->schedule.rank(), c, j, v, *c_off, *c_len) ? 1 : 0;
+        if (!*eligible) return COSMA_B200_OK;
+        *n_pieces = static_cast<int>(v.size());
+        if (pieces && cap >= 3 * *n_pieces)
+            for (size_t i = 0; i < v.size(); ++i) { pieces[3 * i] = v[i].src_off; pieces[3 * i + 1] = v[i].len; pieces[3 * i + 2] = v[i].dst_off; }
+        return COSMA_B200_OK;
     });
 }
 

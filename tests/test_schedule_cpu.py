@@ -140,26 +140,35 @@ def test_column_panels_of_the_local_buffers_are_independent_subproblems(lib, P, 
         assert sub[r].initial_elements[0] == full[r].initial_elements[0]                      # A is shared by all chunks
         assert sub[r].initial_elements[1] * c == full[r].initial_elements[1] and sub[r].initial_elements[2] * c == full[r].initial_elements[2]
         assert len(blocks["B"][r]) == 1 and len(blocks["C"][r]) == 1                          # one column-major block each
-    c_ranges = sorted({(b[0][2], b[0][3] + 1) for b in blocks["C"]})
+    import ctypes
     got = [np.empty_like(w) for w in want]
+    c_ranges = sorted({(b[0][2], b[0][3] + 1) for b in blocks["C"]})
     for j in range(c):
         sa = []
         for r in range(P):
             bufs = [np.zeros(max(sub[r].arena_elements[x], 1)) for x in range(3)]
             bufs[0][:sub[r].initial_elements[0]] = locals_in[r][0]
+            # the pieces as the library plans them (cosma_b200_plan_host_panel) ...
+            pieces, npc = (ctypes.c_int64 * 3000)(), ctypes.c_int(0)
+            coff, clen, ok = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+            assert lib.cosma_b200_plan_host_panel(full[r].handle, c, j, pieces, 3000, ctypes.byref(npc), ctypes.byref(coff), ctypes.byref(clen),
+                                                  ctypes.byref(ok)) == 0 and ok.value == 1
+            planned = [(pieces[3 * i], pieces[3 * i + 1], pieces[3 * i + 2]) for i in range(npc.value)]
+            # ... equal the rule stated above, derived here from the block tables
             (r0, r1, b0, b1) = blocks["B"][r][0]
-            rows, pos = r1 - r0 + 1, 0
-            for (c0, c1) in c_ranges:                       # the C column ranges inside this rank's B columns, in order
+            rows, pos, expect = r1 - r0 + 1, 0, []
+            for (c0, c1) in c_ranges:
                 if c0 < b0 or c1 > b1 + 1:
                     continue
                 w = (c1 - c0) // c
-                assert w * c == c1 - c0
-                lo = (c0 - b0 + j * w) * rows               # contiguous piece of the column-major local B
-                bufs[1][pos:pos + w * rows] = locals_in[r][1][lo:lo + w * rows]
+                expect.append(((c0 - b0 + j * w) * rows, w * rows, pos))
                 pos += w * rows
-            assert pos == sub[r].initial_elements[1]
+            assert planned == expect and pos == sub[r].initial_elements[1]
+            for (src, ln, dst) in planned:
+                bufs[1][dst:dst + ln] = locals_in[r][1][src:src + ln]
             nc = sub[r].initial_elements[2]
-            bufs[2][:nc] = locals_in[r][2][j * nc:(j + 1) * nc]
+            assert (coff.value, clen.value) == (j * nc, nc)
+            bufs[2][:nc] = locals_in[r][2][coff.value:coff.value + nc]
             sa.append(bufs)
         run_schedules(sub, sa, alpha, beta)
         for r in range(P):
@@ -167,5 +176,9 @@ def test_column_panels_of_the_local_buffers_are_independent_subproblems(lib, P, 
             got[r][j * nc:(j + 1) * nc] = sa[r][2][:nc]
     for r in range(P):
         assert np.array_equal(got[r], want[r]), r
+    # layouts that cannot be cut: a width that c does not divide
+    ok = ctypes.c_int(1)
+    assert lib.cosma_b200_plan_host_panel(full[0].handle, 7 if n % 7 else 11, 0, None, 0, ctypes.byref(npc), ctypes.byref(coff), ctypes.byref(clen),
+                                          ctypes.byref(ok)) == 0 and ok.value == 0
     for pl in full + sub:
         pl.destroy()
