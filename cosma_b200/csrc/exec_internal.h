@@ -72,8 +72,9 @@ struct HostOperands {
     const void* C_in = nullptr;
     void* C_out = nullptr;
 };
+// skip_allgather_mask: bit x set = the allgathers of matrix x are skipped (the gathered copy in the arena is still valid)
 int plan_run(Plan& plan, const double* alpha, const double* beta, void* A, void* B, void* C, cudaStream_t stream,
-             const HostOperands* host = nullptr);
+             const HostOperands* host = nullptr, unsigned skip_allgather_mask = 0);
 
 // costa::transform on the device: pack kernel -> grouped ncclSend/ncclRecv -> unpack kernel
 struct TransformPlan {

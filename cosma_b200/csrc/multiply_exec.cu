@@ -131,7 +131,7 @@ int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, char* arena, const
 }  // namespace
 
 int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void* B_, void* C_, cudaStream_t stream,
-             const HostOperands* host) {
+             const HostOperands* host, unsigned skip_allgather_mask) {
     const int E = plan.elem_reals;
     const int64_t EB = plan.elem_bytes();
     char* A = static_cast<char*>(A_);
@@ -175,7 +175,7 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
                 break;
             }
             case cosma::OpKind::ALLGATHER:
-                st = run_allgather(plan, op, arenas[op.matrix], stream);
+                if (!((skip_allgather_mask >> op.matrix) & 1u)) st = run_allgather(plan, op, arenas[op.matrix], stream);
                 break;
             case cosma::OpKind::REDUCE:
                 st = run_reduce(plan, op, arenas[op.matrix], beta, stream);
@@ -225,6 +225,138 @@ bool host_panel_pieces(const cosma::Schedule& schedule, int rank, int c, int j, 
     c_off = j * c_len;
     return true;
 }
+
+// COSMA_B200_HOST_PANELS=c (opt-in until it has run on multi-GPU hardware): the host-pointer multiply of a
+// schedule with collectives as c column panels. A goes up (and is gathered) once; panel j's pieces of B (and of C when beta != 0)
+// travel up on a copy stream while panel j - 1 multiplies, panel j - 1's C travels down on another. Two B / C arena sets alternate.
+// Every decision below depends on global information only (strategy, shapes, c), so all ranks take the same path.
+int host_panels_requested() {
+    static const int c = [] {
+        const char* v = std::getenv("COSMA_B200_HOST_PANELS");
+        const int x = v && *v ? std::atoi(v) : 0;
+        return x > 1 ? x : 0;
+    }();
+    return c;
+}
+
+#define PANEL_CUDA(call)                                                                  \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            set_last_error(std::string("host panels: ") + #call + ": " + cudaGetErrorString(e_)); \
+            return COSMA_B200_CUDA_ERROR;                                                 \
+        }                                                                                 \
+    } while (0)
+
+// *handled = false: the schedule cannot be cut into c panels (same verdict on every rank); the caller takes the plain path.
+int multiply_host_panels(Plan* p, int c, const double* alpha, const double* beta, const void* A, const void* B, void* C, cudaStream_t st,
+                         bool* handled) {
+    *handled = false;
+    if (p->panel_count < 0) return COSMA_B200_OK;  // found unsuitable before
+    if (!p->panel_plan) {
+        p->panel_count = -1;  // until proven suitable
+        const cosma::Strategy& full = p->schedule.strategy();
+        const int P = static_cast<int>(full.P);
+        int n_gemm = 0;
+        bool gathered[3] = {false, false, false};
+        for (const auto& op : p->schedule.ops()) {
+            if (op.kind == cosma::OpKind::GEMM) ++n_gemm;
+            else gathered[op.matrix] = true;
+        }
+        // one GEMM, and an operand that is gathered first (otherwise the plain path already streams A and B under the kernel)
+        if (P < 2 || n_gemm != 1 || !(gathered[0] || gathered[1]) || full.n % c != 0 || p->ring_comms.empty()) return COSMA_B200_OK;
+        std::vector<PanelPiece> probe;
+        std::int64_t o = 0, l = 0;
+        for (int q = 0; q < P; ++q)  // the verdict must not depend on the rank
+            if (!host_panel_pieces(p->schedule, q, c, 0, probe, o, l)) return COSMA_B200_OK;
+        const std::string steps = full.to_string();
+        std::unique_ptr<Plan> sp(new Plan);
+        try {
+            const cosma::Strategy sub = cosma::parse_strategy(full.m, full.n / c, full.k, static_cast<size_t>(P), steps);
+            if (sub.to_string() != steps) return COSMA_B200_OK;
+            sp->schedule = cosma::Schedule(sub, p->schedule.rank());
+        } catch (const std::exception&) {
+            return COSMA_B200_OK;
+        }
+        sp->dtype = p->dtype; sp->elem_reals = p->elem_reals; sp->real_bytes = p->real_bytes;
+        const auto& ra = p->schedule.rings();
+        const auto& rb = sp->schedule.rings();
+        bool same = ra.size() == rb.size();
+        for (size_t i = 0; same && i < ra.size(); ++i) same = ra[i].step == rb[i].step && ra[i].color == rb[i].color && ra[i].my_pos == rb[i].my_pos && ra[i].ranks == rb[i].ranks;
+        if (!same || sp->schedule.initial_elements(0) != p->schedule.initial_elements(0) || sp->schedule.arena_elements(0) > p->schedule.arena_elements(0) ||
+            sp->schedule.initial_elements(1) * c != p->schedule.initial_elements(1) || sp->schedule.initial_elements(2) * c != p->schedule.initial_elements(2))
+            return COSMA_B200_OK;
+        sp->ring_comms = p->ring_comms;  // the same rings: borrowed, destroyed with the parent
+        sp->borrowed_comms = true;
+        p->panel_plan = sp.release();
+        p->panel_count = c;
+    }
+    if (p->panel_count != c) return COSMA_B200_INVALID_ARG;  // one panel count per plan
+    std::vector<PanelPiece> pieces;
+    std::int64_t c_off = 0, c_len = 0;
+    Plan* sp = p->panel_plan;
+    const size_t es = static_cast<size_t>(p->elem_bytes());
+    // arenas: A shared by all panels (large enough for either plan), two sets of the panel plan's B and C arenas
+    const size_t a_bytes = std::max<size_t>(p->schedule.arena_elements(0), 1) * es;
+    if (!p->owned[0]) PANEL_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->owned[0]), a_bytes));
+    for (int s = 0; s < 2; ++s)
+        for (int x = 0; x < 2; ++x)
+            if (!p->panel_arena[s][x])
+                PANEL_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->panel_arena[s][x]), std::max<size_t>(sp->schedule.arena_elements(1 + x), 1) * es));
+    if (!p->panel_in) PANEL_CUDA(cudaStreamCreateWithFlags(&p->panel_in, cudaStreamNonBlocking));
+    if (!p->panel_out) PANEL_CUDA(cudaStreamCreateWithFlags(&p->panel_out, cudaStreamNonBlocking));
+    while (p->panel_ev.size() < static_cast<size_t>(3 + 3 * c)) {
+        cudaEvent_t e;
+        PANEL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->panel_ev.push_back(e);
+    }
+    cudaEvent_t ev_start = p->panel_ev[0], ev_a = p->panel_ev[1], ev_end = p->panel_ev[2];
+    cudaEvent_t* ev_in = p->panel_ev.data() + 3;  // [c] panel j's operands are on the device
+    cudaEvent_t* ev_done = ev_in + c;             // [c] panel j is computed
+    cudaEvent_t* ev_out = ev_done + c;            // [c] panel j's C is back on the host
+    const bool beta_zero = beta[0] == 0.0 && (p->elem_reals == 1 || beta[1] == 0.0);
+    const char* hB = static_cast<const char*>(B);
+    char* hC = static_cast<char*>(C);
+    cudaStream_t cin = p->panel_in, cout = p->panel_out;
+    // the copy streams start after whatever the caller queued on `st` (earlier users of the arenas)
+    PANEL_CUDA(cudaEventRecord(ev_start, st));
+    PANEL_CUDA(cudaStreamWaitEvent(cin, ev_start, 0));
+    PANEL_CUDA(cudaStreamWaitEvent(cout, ev_start, 0));
+    const size_t a_init = static_cast<size_t>(p->schedule.initial_elements(0)) * es;
+    if (a_init) PANEL_CUDA(cudaMemcpyAsync(p->owned[0], A, a_init, cudaMemcpyHostToDevice, cin));
+    PANEL_CUDA(cudaEventRecord(ev_a, cin));
+    p->last_launches = 0;
+    for (int j = 0; j < c; ++j) {
+        const int s = j & 1;
+        char* dB = p->panel_arena[s][0];
+        char* dC = p->panel_arena[s][1];
+        if (!host_panel_pieces(p->schedule, p->schedule.rank(), c, j, pieces, c_off, c_len)) return COSMA_B200_INTERNAL_ERROR;
+        if (j >= 2) {  // set s was last used by panel j - 2: its GEMM read B, its download read C
+            PANEL_CUDA(cudaStreamWaitEvent(cin, ev_done[j - 2], 0));
+            PANEL_CUDA(cudaStreamWaitEvent(cin, ev_out[j - 2], 0));
+            PANEL_CUDA(cudaStreamWaitEvent(st, ev_out[j - 2], 0));
+        }
+        for (const auto& pc : pieces)
+            PANEL_CUDA(cudaMemcpyAsync(dB + pc.dst_off * es, hB + pc.src_off * es, static_cast<size_t>(pc.len) * es, cudaMemcpyHostToDevice, cin));
+        if (!beta_zero && c_len) PANEL_CUDA(cudaMemcpyAsync(dC, hC + c_off * es, static_cast<size_t>(c_len) * es, cudaMemcpyHostToDevice, cin));
+        PANEL_CUDA(cudaEventRecord(ev_in[j], cin));
+        if (j == 0) PANEL_CUDA(cudaStreamWaitEvent(st, ev_a, 0));
+        PANEL_CUDA(cudaStreamWaitEvent(st, ev_in[j], 0));
+        const int rc = plan_run(*sp, alpha, beta, p->owned[0], dB, dC, st, nullptr, j == 0 ? 0u : 1u /* A stays gathered */);
+        if (rc != COSMA_B200_OK) return rc;
+        p->last_launches += sp->last_launches;
+        PANEL_CUDA(cudaEventRecord(ev_done[j], st));
+        PANEL_CUDA(cudaStreamWaitEvent(cout, ev_done[j], 0));
+        if (c_len) PANEL_CUDA(cudaMemcpyAsync(hC + c_off * es, dC, static_cast<size_t>(c_len) * es, cudaMemcpyDeviceToHost, cout));
+        PANEL_CUDA(cudaEventRecord(ev_out[j], cout));
+    }
+    // the caller's stream completes only when the last panel is back on the host
+    PANEL_CUDA(cudaEventRecord(ev_end, cout));
+    PANEL_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
+    *handled = true;
+    return COSMA_B200_OK;
+}
+#undef PANEL_CUDA
 
 }  // namespace cosma_b200
 
@@ -373,11 +505,19 @@ static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int 
 int cosma_b200_plan_destroy(void* plan) {
     Plan* p = static_cast<Plan*>(plan);
     if (!p) return COSMA_B200_OK;
-    for (auto c : p->ring_comms)
-        if (c && nccl()) nccl()->CommDestroy(c);
+    if (!p->borrowed_comms)
+        for (auto c : p->ring_comms)
+            if (c && nccl()) nccl()->CommDestroy(c);
     for (auto e : p->ev) cudaEventDestroy(e);
     for (auto& a : p->owned)
         if (a) cudaFree(a);
+    for (auto e : p->panel_ev) cudaEventDestroy(e);
+    for (auto& set : p->panel_arena)
+        for (auto& a : set)
+            if (a) cudaFree(a);
+    if (p->panel_in) cudaStreamDestroy(p->panel_in);
+    if (p->panel_out) cudaStreamDestroy(p->panel_out);
+    if (p->panel_plan) cosma_b200_plan_destroy(p->panel_plan);
     delete p;
     return COSMA_B200_OK;
 }
@@ -479,6 +619,11 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
         if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
         if (p->schedule.idle()) return COSMA_B200_OK;
         cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (const int panels = cosma_b200::host_panels_requested()) {
+            bool handled = false;
+            const int rc = cosma_b200::multiply_host_panels(p, panels, alpha, beta, A, B, C, st, &handled);
+            if (rc != COSMA_B200_OK || handled) return rc;
+        }
         const size_t es = static_cast<size_t>(p->elem_bytes());
         for (int x = 0; x < 3; ++x)
             if (!p->owned[x]) {

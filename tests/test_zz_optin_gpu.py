@@ -119,3 +119,54 @@ def test_problem_cache_is_bounded(lib):
     out = subprocess.run([sys.executable, "-c", CACHE_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     text = out.stdout + out.stderr
     assert out.returncode == 0 and "RESULT OK" in text, text[-3000:]
+
+
+def _run_world_short(world, cases, env, limit=150):
+    """tests/test_multiply_gpu.py's multi-GPU worker with extra environment and a short wall-clock limit (a hang must cost seconds)."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_multiply_gpu as tm
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = tm._free_port()
+        procs = [ctx.Process(target=tm._worker, args=(r, world, port, cases, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(limit)
+        hung = [p for p in procs if p.is_alive()]
+        for p in hung:
+            p.terminate()
+        assert not hung, "ranks still running after %d s" % limit
+        assert all(p.exitcode == 0 for p in procs)
+        res = q.get(timeout=10)
+        assert all(res), res
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,cases", [
+    (2, [(1000, 2048, 64, "pn2", "d", 1.0, 0.0, "host"), (1000, 2048, 64, "pn2", "d", 2.0, 1.0, "host"), (512, 1536, 96, "pn2", "z", 1.0, 0.0, "host"),
+         (1700, 7000, 96, "pk2", "d", 1.0, 1.0, "host")]),                                   # pk2: nothing is gathered -> the plain streamed path
+    (4, [(1024, 2048, 512, "pn2,pk2", "d", 1.0, 0.0, "host"), (1024, 2048, 512, "pn2,pk2", "d", 1.0, 1.0, "host")]),
+    (8, [(2048, 4096, 2048, "pm2,pn2,pk2", "d", 1.0, 0.0, "host"), (1024, 2048, 1024, "pm2,pn2,pk2", "s", 1.0, 1.0, "host")]),
+])
+def test_host_panels(lib, world, cases):
+    """COSMA_B200_HOST_PANELS=4: cosma_b200_multiply_host as four column panels (A uploaded and gathered once, panels of B up / of C down
+    under the GEMMs). Exact against the dense product, twice per case (arenas, streams and events are reused). Written after the
+    round's GPU budget was spent: the cut itself is proven on the CPU (test_schedule_cpu.py), the stream orchestration has never run,
+    so the test is opt-in (COSMA_B200_TEST_HOST_PANELS=1, tools/gpu_r2_call2_2gpu.sh) like the switch it tests."""
+    if os.environ.get("COSMA_B200_TEST_HOST_PANELS", "0") != "1":
+        pytest.skip("opt-in: COSMA_B200_TEST_HOST_PANELS=1 (not yet run on hardware)")
+    _run_world_short(world, cases, {"COSMA_B200_HOST_PANELS": "4"})
