@@ -272,6 +272,7 @@ int multiply_host_panels(Plan* p, int c, const double* alpha, const double* beta
         const std::string steps = full.to_string();
         std::unique_ptr<Plan> sp(new Plan);
         try {
+            const cosma::Strategy::quiet_errors hush;  // an unsuitable panel shape is an answer, not news
             const cosma::Strategy sub = cosma::parse_strategy(full.m, full.n / c, full.k, static_cast<size_t>(P), steps);
             if (sub.to_string() != steps) return COSMA_B200_OK;
             sp->schedule = cosma::Schedule(sub, p->schedule.rank());
