@@ -195,6 +195,48 @@ __device__ __forceinline__ void transpose_tile(const Shared& sh, const Tile& t, 
     }
 }
 
+// D = S^T staged through a padded shared-memory tile (COSMA_B200_RELAYOUT_SMEM=ON, opt-in until measured): the whole
+// CTA reads the tile along S columns and writes it along D columns, element-sized requests, so a warp request covers 32 consecutive
+// elements on BOTH sides (512 / 256 / 128 contiguous bytes for 16 / 8 / 4-byte elements) where the register transpose above moves
+// 64-128 byte runs. Every thread has TILE / THREADS (4 / 8 / 16) independent loads in flight before the barrier. The row pitch of
+// TILE_ROWS + 1 elements makes the transposed reads conflict-free for all three element sizes. Handles ragged edges by itself.
+template <typename Ops, int TILE_ROWS, int TC>
+__device__ __forceinline__ void transpose_tile_smem(const Shared& sh, const Tile& t, typename Ops::E* tile) {
+    using E = typename Ops::E;
+    constexpr int PITCH = TILE_ROWS + 1;
+    constexpr int PER_THREAD = TILE_ROWS * TC / THREADS;
+    static_assert(TILE_ROWS * TC % THREADS == 0 && THREADS % TILE_ROWS == 0 && THREADS % TC == 0, "tile shape");
+    const E* __restrict__ src = reinterpret_cast<const E*>(sh.p.src);
+    E* __restrict__ dst = reinterpret_cast<E*>(sh.p.dst);
+    const long long sld = sh.p.src_ld, dld = sh.p.dst_ld;
+    __syncthreads();  // the previous tile has left shared memory
+    {
+        E v[PER_THREAD];
+#pragma unroll
+        for (int q = 0; q < PER_THREAD; ++q) {
+            const int idx = threadIdx.x + q * THREADS;
+            const int r = idx % TILE_ROWS, c = idx / TILE_ROWS;
+            if (r < t.nr && c < t.nc) v[q] = src[(t.r0 + r) + (t.c0 + c) * sld];
+        }
+#pragma unroll
+        for (int q = 0; q < PER_THREAD; ++q) {
+            const int idx = threadIdx.x + q * THREADS;
+            const int r = idx % TILE_ROWS, c = idx / TILE_ROWS;
+            if (r < t.nr && c < t.nc) tile[c * PITCH + r] = v[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER_THREAD; ++q) {
+        const int idx = threadIdx.x + q * THREADS;
+        const int c = idx % TC, r = idx / TC;  // D(c, r) = S(r, c): consecutive lanes walk a D column
+        if (r < t.nr && c < t.nc) {
+            E* d = dst + (t.c0 + c) + (t.r0 + r) * dld;
+            *d = finish<Ops>(sh, tile[c * PITCH + r], d);
+        }
+    }
+}
+
 // Edge tiles whose extent is not a whole number of 16-byte vectors: plain element loop (rare, small).
 template <typename Ops, bool TRANSPOSE>
 __device__ __forceinline__ void ragged_tile(const Shared& sh, const Tile& t) {
@@ -212,12 +254,13 @@ __device__ __forceinline__ void ragged_tile(const Shared& sh, const Tile& t) {
     }
 }
 
-template <typename Ops, bool TRANSPOSE, int VEC>
+template <typename Ops, bool TRANSPOSE, int VEC, bool SMEM = false>
 __global__ void __launch_bounds__(THREADS, 6) relayout_kernel(const DevPiece* __restrict__ pieces, const DevScalars* __restrict__ scalars,
                                                                int n_pieces, long long total_tiles, long long tiles_per_cta, int lr_shift) {
     using E = typename Ops::E;
     constexpr int TILE_ROWS = relayout_tile_rows(sizeof(E), TRANSPOSE), TC = relayout_tile_cols(sizeof(E), TRANSPOSE);
     __shared__ Shared sh;
+    __shared__ alignas(16) unsigned char tile_mem[SMEM ? (TILE_ROWS + 1) * TC * sizeof(E) : 16];
     long long t = static_cast<long long>(blockIdx.x) * tiles_per_cta;
     const long long t_end = min(total_tiles, t + tiles_per_cta);
     if (t >= t_end) return;
@@ -257,7 +300,8 @@ __global__ void __launch_bounds__(THREADS, 6) relayout_kernel(const DevPiece* __
         tc.c0 = (lt / tiles_r) * TC;
         tc.nr = min(TILE_ROWS, sh.p.rows - tc.r0);
         tc.nc = min(TC, sh.p.cols - tc.c0);
-        if (VEC > 1 && (tc.nr % VEC != 0 || tc.nc % VEC != 0)) ragged_tile<Ops, TRANSPOSE>(sh, tc);
+        if (SMEM) transpose_tile_smem<Ops, TILE_ROWS, TC>(sh, tc, reinterpret_cast<E*>(tile_mem));
+        else if (VEC > 1 && (tc.nr % VEC != 0 || tc.nc % VEC != 0)) ragged_tile<Ops, TRANSPOSE>(sh, tc);
         else if (TRANSPOSE) transpose_tile<Ops, VEC, TILE_ROWS, TC>(sh, tc, lr_shift);
         else copy_tile<Ops, VEC, TILE_ROWS, TC>(sh, tc);
     }
@@ -266,11 +310,13 @@ __global__ void __launch_bounds__(THREADS, 6) relayout_kernel(const DevPiece* __
 // Tunables (defaults chosen from measurements on B200, profiles/; overridable for experiments):
 //   COSMA_B200_RELAYOUT_LR = 4 | 8 | 16   rows of the lane grid used by transposes
 struct Tuning {
+    bool smem_transpose = false;  // COSMA_B200_RELAYOUT_SMEM=ON: transposes through a shared-memory tile (opt-in until measured)
     int lr_shift = 2;  // 4 x 8 lane grid: 64-byte read runs, 128-byte write runs (best of 4|8|16 on B200, profiles/r1_relayout_sweep.txt)
 };
 const Tuning& tuning() {
     static Tuning t = [] {
         Tuning v;
+        if (const char* e = std::getenv("COSMA_B200_RELAYOUT_SMEM")) v.smem_transpose = e[0] == 'O' && e[1] == 'N';
         if (const char* e = std::getenv("COSMA_B200_RELAYOUT_LR")) {
             const int lr = std::atoi(e);
             v.lr_shift = lr == 8 ? 3 : lr == 16 ? 4 : lr == 2 ? 1 : 2;
@@ -374,12 +420,12 @@ void relayout_free(RelayoutBatch& b) {
 }
 
 namespace {
-template <typename Ops, bool TRANSPOSE, int VEC>
+template <typename Ops, bool TRANSPOSE, int VEC, bool SMEM = false>
 int launch_class(const DevPiece* pieces, int n_pieces, std::int64_t tiles, const DevScalars* scalars, cudaStream_t stream) {
     // grid = SMs x resident CTAs (no partial wave); every CTA walks a contiguous range of tiles
     static int resident = 0;
     if (resident == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, relayout_kernel<Ops, TRANSPOSE, VEC>, THREADS, 0) != cudaSuccess || resident <= 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, relayout_kernel<Ops, TRANSPOSE, VEC, SMEM>, THREADS, 0) != cudaSuccess || resident <= 0) {
             cudaGetLastError();
             resident = 6;
         }
@@ -388,7 +434,7 @@ int launch_class(const DevPiece* pieces, int n_pieces, std::int64_t tiles, const
     long long ctas = std::min<long long>(tiles, max_ctas);
     const long long per = (tiles + ctas - 1) / ctas;
     ctas = (tiles + per - 1) / per;
-    relayout_kernel<Ops, TRANSPOSE, VEC><<<dim3(static_cast<unsigned>(ctas)), dim3(THREADS), 0, stream>>>(pieces, scalars, n_pieces, tiles, per, tuning().lr_shift);
+    relayout_kernel<Ops, TRANSPOSE, VEC, SMEM><<<dim3(static_cast<unsigned>(ctas)), dim3(THREADS), 0, stream>>>(pieces, scalars, n_pieces, tiles, per, tuning().lr_shift);
     if (cudaGetLastError() != cudaSuccess) {
         set_last_error("relayout: kernel launch failed");
         return COSMA_B200_CUDA_ERROR;
@@ -405,8 +451,14 @@ int launch_typed(const RelayoutBatch& b, cudaStream_t stream, int* launches) {
         switch (c) {
             case 0: st = launch_class<Ops, false, 1>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream); break;
             case 1: st = launch_class<Ops, false, VEC>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream); break;
-            case 2: st = launch_class<Ops, true, 1>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream); break;
-            default: st = launch_class<Ops, true, VEC>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream); break;
+            case 2:
+                st = tuning().smem_transpose ? launch_class<Ops, true, 1, true>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream)
+                                             : launch_class<Ops, true, 1>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream);
+                break;
+            default:
+                st = tuning().smem_transpose ? launch_class<Ops, true, VEC, true>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream)
+                                             : launch_class<Ops, true, VEC>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream);
+                break;
         }
         if (st != COSMA_B200_OK) return st;
         if (launches) ++*launches;

@@ -21,6 +21,9 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm
     python tools/gemm_time.py --dtype z --m 8192 --n 8192 --k 8192 --reps 1 > gpurun_out/ncu_zgemm.log 2>&1
 # 4. relayout sweep and the COSTA miniapps from host memory (GB/s of matrix bytes, end to end)
 timeout 200 python tools/relayout_bench.py --n 16384 > gpurun_out/r2_relayout_sweep.txt 2>&1
+# 4b. the shared-memory transpose variant: bit-exact suite under the switch, then the same sweep (transposes only)
+COSMA_B200_RELAYOUT_SMEM=ON timeout 200 python -m pytest tests/test_costa_gpu.py -m gpu -q -k "not gpus" > gpurun_out/r2_pytest_costa_smem.txt 2>&1; tail -2 gpurun_out/r2_pytest_costa_smem.txt
+COSMA_B200_RELAYOUT_SMEM=ON timeout 200 python tools/relayout_bench.py --n 16384 --cases transpose,conj_transpose --tag smem > gpurun_out/r2_relayout_sweep_smem.txt 2>&1
 for t in double zdouble; do
   timeout 100 python -m cosma_b200.launch -np 1 tests/cpp/bin/pxgemr2d_miniapp -m 16384 -n 16384 --block_a 256,256 --block_c 128,512 -t $t -r 4 >> gpurun_out/r2_costa_miniapps.txt 2>&1
   timeout 100 python -m cosma_b200.launch -np 1 tests/cpp/bin/pxtran_miniapp -m 16384 -n 16384 --block_a 256,256 --block_c 128,512 -t $t --op C -r 4 >> gpurun_out/r2_costa_miniapps.txt 2>&1
