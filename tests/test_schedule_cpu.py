@@ -182,3 +182,76 @@ def test_column_panels_of_the_local_buffers_are_independent_subproblems(lib, P, 
                                           ctypes.byref(ok)) == 0 and ok.value == 0
     for pl in full + sub:
         pl.destroy()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12])   # seed 7 draws no eligible layout at all
+def test_column_panels_randomised(lib, seed):
+    """Random shapes, rank counts, strategies (automatic and explicit, parallel and sequential steps) and panel counts: whenever
+    cosma_b200_plan_host_panel calls a layout eligible on EVERY rank and the sub-problem keeps the strategy, the panels planned by the
+    library reproduce the full product bit for bit in lock-step. (Idle ranks, several GEMMs, several blocks per rank, indivisible widths
+    must come back as not eligible -- never as a wrong product.)"""
+    import ctypes
+    import numpy as np
+    from cosma_b200 import planning
+    from cosma_b200.distributed import MultiplyPlan, fill_local_from_global
+    from schedule_sim import run_schedules
+    rng = np.random.default_rng(7000 + seed)
+    checked = 0
+    for _ in range(10):
+        P = int(rng.choice([2, 3, 4, 6, 8, 12]))
+        c = int(rng.choice([2, 3, 4]))
+        m, k = int(rng.integers(8, 60)), int(rng.integers(8, 60))
+        n = c * P * int(rng.integers(1, 5))
+        explicit = {2: ["pk2", "pn2", "pm2"], 3: ["pn3", "pk3"], 4: ["pn2,pk2", "pm2,pn2", "pk2,pn2", "pn4"], 6: ["pn2,pk3", "pm3,pn2"],
+                    8: ["pm2,pn2,pk2", "pn2,pn2,pk2", "pk2,pm2,pn2", "sm2,pn2,pk4"], 12: ["pm2,pn2,pk3", "pn3,pk4"]}[P]
+        steps = str(rng.choice(explicit + [""]))
+        try:
+            full = [MultiplyPlan(None, m, n, k, steps, "d", rank=r, nranks=P, allocate=False) for r in range(P)]
+        except Exception:
+            continue
+        real_steps = full[0].strategy
+        verdicts = []
+        for r in range(P):
+            npc, coff, clen, ok = ctypes.c_int(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+            assert lib.cosma_b200_plan_host_panel(full[r].handle, c, 0, None, 0, ctypes.byref(npc), ctypes.byref(coff), ctypes.byref(clen), ctypes.byref(ok)) == 0
+            verdicts.append(ok.value)
+        used = full[0].P_used
+        one_gemm = all(sum(op["kind"] == "gemm" for op in full[r].ops()) == 1 for r in range(used))
+        try:
+            sub = [MultiplyPlan(None, m, n // c, k, real_steps, "d", rank=r, nranks=P, allocate=False) for r in range(P)] if real_steps else None
+        except Exception:
+            sub = None
+        if used == P and all(verdicts) and one_gemm and sub is not None and sub[0].strategy == real_steps and \
+                all(sub[r].initial_elements[1] * c == full[r].initial_elements[1] and sub[r].initial_elements[2] * c == full[r].initial_elements[2]
+                    and sub[r].initial_elements[0] == full[r].initial_elements[0] for r in range(P)):
+            Ag, Bg = rng.integers(-5, 6, size=(m, k)).astype(np.float64), rng.integers(-5, 6, size=(k, n)).astype(np.float64)
+            Cg = rng.integers(-5, 6, size=(m, n)).astype(np.float64)
+            arenas = []
+            for pl in full:
+                bufs = [np.zeros(max(pl.arena_elements[x], 1)) for x in range(3)]
+                for x, (label, G) in enumerate((("A", Ag), ("B", Bg), ("C", Cg))):
+                    fill_local_from_global(pl, label, bufs[x], G)
+                arenas.append(bufs)
+            locals_in = [[a[x][:pl.initial_elements[x]].copy() for x in range(3)] for a, pl in zip(arenas, full)]
+            run_schedules(full, arenas, 1.0, 1.0)
+            for j in range(c):
+                sa = []
+                for r in range(P):
+                    bufs = [np.zeros(max(sub[r].arena_elements[x], 1)) for x in range(3)]
+                    bufs[0][:sub[r].initial_elements[0]] = locals_in[r][0]
+                    pieces, npc = (ctypes.c_int64 * 3000)(), ctypes.c_int(0)
+                    coff, clen, ok = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+                    lib.cosma_b200_plan_host_panel(full[r].handle, c, j, pieces, 3000, ctypes.byref(npc), ctypes.byref(coff), ctypes.byref(clen), ctypes.byref(ok))
+                    for i in range(npc.value):
+                        src, ln, dst = pieces[3 * i], pieces[3 * i + 1], pieces[3 * i + 2]
+                        bufs[1][dst:dst + ln] = locals_in[r][1][src:src + ln]
+                    bufs[2][:clen.value] = locals_in[r][2][coff.value:coff.value + clen.value]
+                    sa.append(bufs)
+                run_schedules(sub, sa, 1.0, 1.0)
+                for r in range(P):
+                    nc = sub[r].initial_elements[2]
+                    assert np.array_equal(sa[r][2][:nc], arenas[r][2][j * nc:(j + 1) * nc]), (P, real_steps, m, n, k, c, j, r)
+            checked += 1
+        for pl in full + (sub or []):
+            pl.destroy()
+    assert checked >= 1
