@@ -17,6 +17,10 @@ except Exception as e:
     print(sys.argv[1], "no line:", e)
 PY
 }
+# how much of the host link each rank keeps when eight share the host, without and with NUMA placement
+timeout 60 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29582 tools/pcie_probe.py > gpurun_out/r2_pcie_probe_n8.jsonl 2>&1
+timeout 60 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29583 tools/pcie_probe.py --bind > gpurun_out/r2_pcie_probe_n8_bound.jsonl 2>&1
+grep -h h2d_contig gpurun_out/r2_pcie_probe_n8.jsonl gpurun_out/r2_pcie_probe_n8_bound.jsonl | cut -c1-200 | head -4
 run_bench plain COSMA_B200_HOST_PANELS=0
 run_bench panels4 COSMA_B200_HOST_PANELS=4
 run_bench panels8 COSMA_B200_HOST_PANELS=8
