@@ -123,6 +123,24 @@ COSMA_B200_WEAK void Cblacs_gridexit(int ictxt) {
 
 COSMA_B200_WEAK void Cblacs_exit(int) {}
 
+// The Fortran entry points of the same calls (all arguments by reference, trailing underscore; character arguments carry a hidden
+// length that is not read) -- what a Fortran ScaLAPACK application calls before p?gemm_ when this library stands in for BLACS.
+COSMA_B200_WEAK void blacs_pinfo_(int* mypnum, int* nprocs) { Cblacs_pinfo(mypnum, nprocs); }
+COSMA_B200_WEAK void blacs_get_(const int* ictxt, const int* what, int* val) { Cblacs_get(*ictxt, *what, val); }
+COSMA_B200_WEAK void blacs_gridinit_(int* ictxt, const char* order, const int* nprow, const int* npcol) {
+    char o = order ? *order : 'R';
+    Cblacs_gridinit(ictxt, &o, *nprow, *npcol);
+}
+COSMA_B200_WEAK void blacs_gridinfo_(const int* ictxt, int* nprow, int* npcol, int* myrow, int* mycol) { Cblacs_gridinfo(*ictxt, nprow, npcol, myrow, mycol); }
+COSMA_B200_WEAK int blacs_pnum_(const int* ictxt, const int* prow, const int* pcol) { return Cblacs_pnum(*ictxt, *prow, *pcol); }
+COSMA_B200_WEAK void blacs_pcoord_(const int* ictxt, const int* pnum, int* prow, int* pcol) { Cblacs_pcoord(*ictxt, *pnum, prow, pcol); }
+COSMA_B200_WEAK void blacs_barrier_(const int* ictxt, const char* scope) {
+    char sc = scope ? *scope : 'A';
+    Cblacs_barrier(*ictxt, &sc);
+}
+COSMA_B200_WEAK void blacs_gridexit_(const int* ictxt) { Cblacs_gridexit(*ictxt); }
+COSMA_B200_WEAK void blacs_exit_(const int* cont) { Cblacs_exit(*cont); }
+
 // ScaLAPACK tools
 COSMA_B200_WEAK void descinit_(int* desc, const int* m, const int* n, const int* mb, const int* nb, const int* irsrc, const int* icsrc,
                                const int* ictxt, const int* lld, int* info) {

@@ -23,6 +23,14 @@ extern "C" {
 void descinit_(int* desc, const int* m, const int* n, const int* mb, const int* nb, const int* irsrc, const int* icsrc, const int* ictxt,
                const int* lld, int* info);
 int numroc_(const int* n, const int* nb, const int* iproc, const int* isrcproc, const int* nprocs);
+// the Fortran entry points of BLACS (libcosma_blacs_lite.so supplies them when no BLACS is linked)
+void blacs_pinfo_(int* mypnum, int* nprocs);
+void blacs_get_(const int* ictxt, const int* what, int* val);
+void blacs_gridinit_(int* ictxt, const char* order, const int* nprow, const int* npcol);
+void blacs_gridinfo_(const int* ictxt, int* nprow, int* npcol, int* myrow, int* mycol);
+int blacs_pnum_(const int* ictxt, const int* prow, const int* pcol);
+void blacs_pcoord_(const int* ictxt, const int* pnum, int* prow, int* pcol);
+void blacs_gridexit_(const int* ictxt);
 }
 
 template <typename T> struct real_of { using type = T; };
@@ -144,6 +152,24 @@ int main(int argc, char** argv) {
     gemr2d_case<zd, gemr2d_d>(row_major, col_major, costa_pzgemr2d_, 27, 27, 3, 3, 1, 2, "costa_pzgemr2d_ R -> C");
     gemr2d_case<zf, gemr2d_s>(col_major, row_major, pcgemr2d_, 19, 50, 1, 1, 5, 1, "pcgemr2d_ C -> R");
 
+    {   // a grid set up the way a Fortran application does it: same numbering as the C calls, and the wrappers work on it
+        int me = -1, np = 0, ctxt = 0;
+        const int zero = 0;
+        blacs_pinfo_(&me, &np);
+        CHECK_MSG(me == rank && np == P, "blacs_pinfo_");
+        blacs_get_(&zero, &zero, &ctxt);
+        blacs_gridinit_(&ctxt, "Col-major", &nprow, &npcol);
+        int r1, c1, pr, pc, r2, c2, pr2, pc2;
+        blacs_gridinfo_(&ctxt, &r1, &c1, &pr, &pc);
+        cosma::blacs::Cblacs_gridinfo(ctxt, &r2, &c2, &pr2, &pc2);
+        CHECK_MSG(r1 == nprow && c1 == npcol && r1 == r2 && c1 == c2 && pr == pr2 && pc == pc2, "blacs_gridinfo_ == Cblacs_gridinfo");
+        CHECK_MSG(blacs_pnum_(&ctxt, &pr, &pc) == rank, "blacs_pnum_ of my coordinates");
+        int qr = -1, qc = -1;
+        blacs_pcoord_(&ctxt, &rank, &qr, &qc);
+        CHECK_MSG(qr == pr && qc == pc && rank == pc * nprow + pr, "blacs_pcoord_ (column-major numbering)");
+        tran_case<double, tran_d>(ctxt, pdtran_, false, 26, 31, 2, 1, 1, 3, 1.0, 0.0, "pdtran_ on a grid from blacs_gridinit_");
+        blacs_gridexit_(&ctxt);
+    }
     cosma::pxgemm_release_grids();
     cosma::blacs::Cblacs_gridexit(row_major);
     cosma::blacs::Cblacs_gridexit(col_major);

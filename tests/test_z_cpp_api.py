@@ -96,6 +96,10 @@ def test_host_libraries_export_the_reference_symbols(host_libs):
             assert " T %s\n" % name in sc, name
         for name in ("costa_" + low, "costa_" + low + "_", "COSTA_" + low.upper(), "COSTA_" + low.upper() + "_"):
             assert " T %s\n" % name in psc, name
+    bl = symbols("libcosma_blacs_lite.so")
+    for name in ("Cblacs_gridinit", "Cblacs_gridinfo", "Cblacs2sys_handle", "Cblacs_pcoord", "blacs_gridinit_", "blacs_gridinfo_", "blacs_pinfo_",
+                 "blacs_get_", "blacs_pnum_", "blacs_pcoord_", "blacs_barrier_", "blacs_gridexit_", "blacs_exit_", "descinit_", "numroc_"):
+        assert " W %s\n" % name in bl, name   # weak: a real BLACS takes precedence
     cpp = symbols("libcosma_pxgemm_cpp.so")
     assert "void costa::pxgemr2d<double>(int, int, double const*" in cpp and "void costa::pxtran_op<std::complex<float>>(" in cpp
     assert "void cosma::pxgemm<double>(char, char, int, int, int, double, double const*" in cpp
