@@ -198,7 +198,7 @@ __device__ __forceinline__ void transpose_tile(const Shared& sh, const Tile& t, 
 // D = S^T staged through a padded shared-memory tile (COSMA_B200_RELAYOUT_SMEM=ON, opt-in until measured): the whole
 // CTA reads the tile along S columns and writes it along D columns, element-sized requests, so a warp request covers 32 consecutive
 // elements on BOTH sides (512 / 256 / 128 contiguous bytes for 16 / 8 / 4-byte elements) where the register transpose above moves
-// 64-128 byte runs. Every thread has TILE / THREADS (4 / 8 / 16) independent loads in flight before the barrier. The row pitch of
+// 64-128 byte runs. Every thread has 4 / 8 / 8 independent loads in flight (16 / 8 / 4-byte elements) before it stores to shared memory. The row pitch of
 // TILE_ROWS + 1 elements makes the transposed reads conflict-free for all three element sizes. Handles ragged edges by itself.
 template <typename Ops, int TILE_ROWS, int TC>
 __device__ __forceinline__ void transpose_tile_smem(const Shared& sh, const Tile& t, typename Ops::E* tile) {
@@ -210,17 +210,19 @@ __device__ __forceinline__ void transpose_tile_smem(const Shared& sh, const Tile
     E* __restrict__ dst = reinterpret_cast<E*>(sh.p.dst);
     const long long sld = sh.p.src_ld, dld = sh.p.dst_ld;
     __syncthreads();  // the previous tile has left shared memory
-    {
-        E v[PER_THREAD];
+    constexpr int BATCH = PER_THREAD > 8 ? 8 : PER_THREAD;  // loads in flight per thread (more would spill at 40 registers)
+#pragma unroll 1
+    for (int base = 0; base < PER_THREAD; base += BATCH) {
+        E v[BATCH];
 #pragma unroll
-        for (int q = 0; q < PER_THREAD; ++q) {
-            const int idx = threadIdx.x + q * THREADS;
+        for (int q = 0; q < BATCH; ++q) {
+            const int idx = threadIdx.x + (base + q) * THREADS;
             const int r = idx % TILE_ROWS, c = idx / TILE_ROWS;
             if (r < t.nr && c < t.nc) v[q] = src[(t.r0 + r) + (t.c0 + c) * sld];
         }
 #pragma unroll
-        for (int q = 0; q < PER_THREAD; ++q) {
-            const int idx = threadIdx.x + q * THREADS;
+        for (int q = 0; q < BATCH; ++q) {
+            const int idx = threadIdx.x + (base + q) * THREADS;
             const int r = idx % TILE_ROWS, c = idx / TILE_ROWS;
             if (r < t.nr && c < t.nc) tile[c * PITCH + r] = v[q];
         }
