@@ -131,6 +131,26 @@ def main(argv=None):
     print("per rank (worst): device arenas %.2f GB, wire %.1f MB, GEMM %.2f TFLOP" % (d["arena_bytes"] / 1e9, d["wire_bytes"] / 1e6, d["flops"] / 1e12))
     print("estimate  : GEMM %.2f ms + collectives %.2f ms (not overlapped) -> %.1f %% of the step is communication" %
           (d["t_gemm_ms"], d["t_wire_ms"], 100.0 * d["t_wire_ms"] / max(d["t_gemm_ms"] + d["t_wire_ms"], 1e-12)))
+    if a.P > 1 and d["strategy"]:
+        # can the host-memory entry point run this schedule as pipelined column panels (COSMA_B200_HOST_PANELS)?
+        import ctypes
+        code = BYTES[a.type][0]
+        ok_for = []
+        for c in (2, 4, 8):
+            verdicts = []
+            for r in range(d["P_used"]):
+                pl = MultiplyPlan(None, a.m, a.n, a.k, a.steps, code, rank=r, nranks=a.P, allocate=False)
+                npc, coff, clen, ok = ctypes.c_int(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+                pl.lib.cosma_b200_plan_host_panel(pl.handle, c, 0, None, 0, ctypes.byref(npc), ctypes.byref(coff), ctypes.byref(clen), ctypes.byref(ok))
+                n_gemm = sum(op["kind"] == "gemm" for op in pl.ops())
+                verdicts.append(bool(ok.value) and n_gemm == 1)
+                pl.destroy()
+                if not verdicts[-1] or r >= 7:
+                    break
+            if verdicts and all(verdicts):
+                ok_for.append(c)
+        print("host panels: %s" % ("local B / C can be cut into %s column panels (cosma_b200_plan_host_panel)" % " / ".join(map(str, ok_for)) if ok_for
+                                   else "layout cannot be cut into column panels"))
     if a.layout:
         _, grids = layouts(a.m, a.n, a.k, a.P, a.steps)
         for label in "ABC":
