@@ -54,16 +54,18 @@ struct Plan {
     std::vector<cudaEvent_t> panel_ev;
 };
 
-// One piece of a rank's local B that belongs to column panel j: `len` elements from src_off of the local buffer go to dst_off of the
-// panel's local B.
+// One piece of a rank's local B (or C) that belongs to column panel j: `len` elements from src_off of the local buffer correspond to
+// dst_off of the panel's local buffer.
 struct PanelPiece {
     std::int64_t src_off, len, dst_off;
 };
-// Column panel j of c of this rank's local matrices: local C columns [j, j+1) * (width / c) -- contiguous -- and,
-// for every C column range of the ranks that lies inside this rank's B columns, the j-th c-th of it. False when the layout does not
-// allow it (several blocks per rank, widths not divisible by c, C ranges that do not tile the B columns).
-bool host_panel_pieces(const cosma::Schedule& schedule, int rank, int c, int j, std::vector<PanelPiece>& b_pieces, std::int64_t& c_off,
-                       std::int64_t& c_len);
+// Column panel j of c of this rank's local matrices. The column ranges of all ranks' B blocks and C blocks are
+// refined into elementary ranges (each inside one B range and one C range); panel j takes the j-th c-th of every elementary range:
+// of local B those inside the rank's B columns, of local C those inside its C columns, each a contiguous piece of the column-major
+// local buffer, concatenated in column order. False when the layout does not allow it (several blocks per rank, a width that c does
+// not divide).
+bool host_panel_pieces(const cosma::Schedule& schedule, int rank, int c, int j, std::vector<PanelPiece>& b_pieces,
+                       std::vector<PanelPiece>& c_pieces);
 
 // host copies of the local matrices for the one GEMM of a schedule that can stream them (multiply_exec.cu)
 struct HostOperands {

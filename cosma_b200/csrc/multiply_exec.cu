@@ -188,41 +188,37 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
     return COSMA_B200_OK;
 }
 
-bool host_panel_pieces(const cosma::Schedule& schedule, int rank, int c, int j, std::vector<PanelPiece>& b_pieces, std::int64_t& c_off,
-                       std::int64_t& c_len) {
+bool host_panel_pieces(const cosma::Schedule& schedule, int rank, int c, int j, std::vector<PanelPiece>& b_pieces,
+                       std::vector<PanelPiece>& c_pieces) {
     b_pieces.clear();
+    c_pieces.clear();
     const int P = static_cast<int>(schedule.strategy().P);
     if (c < 1 || j < 0 || j >= c || rank < 0 || rank >= P) return false;
-    const auto& myB = schedule.mapper(1).initial_layout(rank);
-    const auto& myC = schedule.mapper(2).initial_layout(rank);
-    if (myB.size() != 1 || myC.size() != 1) return false;
-    std::vector<std::pair<int, int>> ranges;  // distinct [first, last] column ranges of the ranks' C blocks
-    for (int q = 0; q < P; ++q) {
-        const auto& blocks = schedule.mapper(2).initial_layout(q);
-        if (blocks.size() != 1) return false;
-        ranges.emplace_back(blocks[0].cols.first(), blocks[0].cols.last());
-    }
-    std::sort(ranges.begin(), ranges.end());
-    ranges.erase(std::unique(ranges.begin(), ranges.end()), ranges.end());
-    const std::int64_t b0 = myB[0].cols.first(), b1 = myB[0].cols.last(), rows = myB[0].rows.length();
-    std::int64_t pos = 0, covered = 0;
-    for (const auto& rg : ranges) {
-        if (rg.first < b0 || rg.second > b1) {
-            if (rg.second >= b0 && rg.first <= b1) return false;  // straddles the edge of this rank's B columns
-            continue;
+    // elementary column ranges: consecutive cuts of the union of all B and C block boundaries
+    std::vector<int> cuts;
+    for (int x = 1; x <= 2; ++x)
+        for (int q = 0; q < P; ++q) {
+            const auto& blocks = schedule.mapper(x).initial_layout(q);
+            if (blocks.size() != 1) return false;
+            cuts.push_back(blocks[0].cols.first());
+            cuts.push_back(blocks[0].cols.last() + 1);
         }
-        const std::int64_t width = rg.second - rg.first + 1;
-        if (width % c != 0) return false;
-        const std::int64_t w = width / c;
-        b_pieces.push_back(PanelPiece{(rg.first - b0 + j * w) * rows, w * rows, pos});
-        pos += w * rows;
-        covered += width;
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    for (size_t i = 0; i + 1 < cuts.size(); ++i)
+        if ((cuts[i + 1] - cuts[i]) % c != 0) return false;
+    for (int x = 1; x <= 2; ++x) {
+        const auto& mine = schedule.mapper(x).initial_layout(rank)[0];
+        const std::int64_t first = mine.cols.first(), last = mine.cols.last(), rows = mine.rows.length();
+        std::vector<PanelPiece>& out = x == 1 ? b_pieces : c_pieces;
+        std::int64_t pos = 0;
+        for (size_t i = 0; i + 1 < cuts.size(); ++i) {
+            if (cuts[i] < first || cuts[i + 1] > last + 1) continue;  // block boundaries are cuts: an elementary range is inside or outside
+            const std::int64_t w = (cuts[i + 1] - cuts[i]) / c;
+            out.push_back(PanelPiece{(cuts[i] - first + j * w) * rows, w * rows, pos});
+            pos += w * rows;
+        }
     }
-    if (covered != b1 - b0 + 1) return false;
-    const std::int64_t cw = myC[0].cols.length();
-    if (cw % c != 0) return false;
-    c_len = (cw / c) * static_cast<std::int64_t>(myC[0].rows.length());
-    c_off = j * c_len;
     return true;
 }
 
@@ -265,10 +261,9 @@ int multiply_host_panels(Plan* p, int c, const double* alpha, const double* beta
         }
         // one GEMM, and an operand that is gathered first (otherwise the plain path already streams A and B under the kernel)
         if (P < 2 || n_gemm != 1 || !(gathered[0] || gathered[1]) || full.n % c != 0 || p->ring_comms.empty()) return COSMA_B200_OK;
-        std::vector<PanelPiece> probe;
-        std::int64_t o = 0, l = 0;
+        std::vector<PanelPiece> probe_b, probe_c;
         for (int q = 0; q < P; ++q)  // the verdict must not depend on the rank
-            if (!host_panel_pieces(p->schedule, q, c, 0, probe, o, l)) return COSMA_B200_OK;
+            if (!host_panel_pieces(p->schedule, q, c, 0, probe_b, probe_c)) return COSMA_B200_OK;
         const std::string steps = full.to_string();
         std::unique_ptr<Plan> sp(new Plan);
         try {
@@ -293,8 +288,7 @@ int multiply_host_panels(Plan* p, int c, const double* alpha, const double* beta
         p->panel_count = c;
     }
     if (p->panel_count != c) return COSMA_B200_INVALID_ARG;  // one panel count per plan
-    std::vector<PanelPiece> pieces;
-    std::int64_t c_off = 0, c_len = 0;
+    std::vector<PanelPiece> pieces, cpieces;
     Plan* sp = p->panel_plan;
     const size_t es = static_cast<size_t>(p->elem_bytes());
     // arenas: A shared by all panels (large enough for either plan), two sets of the panel plan's B and C arenas
@@ -331,7 +325,7 @@ int multiply_host_panels(Plan* p, int c, const double* alpha, const double* beta
         const int s = j & 1;
         char* dB = p->panel_arena[s][0];
         char* dC = p->panel_arena[s][1];
-        if (!host_panel_pieces(p->schedule, p->schedule.rank(), c, j, pieces, c_off, c_len)) return COSMA_B200_INTERNAL_ERROR;
+        if (!host_panel_pieces(p->schedule, p->schedule.rank(), c, j, pieces, cpieces)) return COSMA_B200_INTERNAL_ERROR;
         if (j >= 2) {  // set s was last used by panel j - 2: its GEMM read B, its download read C
             PANEL_CUDA(cudaStreamWaitEvent(cin, ev_done[j - 2], 0));
             PANEL_CUDA(cudaStreamWaitEvent(cin, ev_out[j - 2], 0));
@@ -339,7 +333,9 @@ int multiply_host_panels(Plan* p, int c, const double* alpha, const double* beta
         }
         for (const auto& pc : pieces)
             PANEL_CUDA(cudaMemcpyAsync(dB + pc.dst_off * es, hB + pc.src_off * es, static_cast<size_t>(pc.len) * es, cudaMemcpyHostToDevice, cin));
-        if (!beta_zero && c_len) PANEL_CUDA(cudaMemcpyAsync(dC, hC + c_off * es, static_cast<size_t>(c_len) * es, cudaMemcpyHostToDevice, cin));
+        if (!beta_zero)
+            for (const auto& pc : cpieces)
+                PANEL_CUDA(cudaMemcpyAsync(dC + pc.dst_off * es, hC + pc.src_off * es, static_cast<size_t>(pc.len) * es, cudaMemcpyHostToDevice, cin));
         PANEL_CUDA(cudaEventRecord(ev_in[j], cin));
         if (j == 0) PANEL_CUDA(cudaStreamWaitEvent(st, ev_a, 0));
         PANEL_CUDA(cudaStreamWaitEvent(st, ev_in[j], 0));
@@ -348,7 +344,8 @@ int multiply_host_panels(Plan* p, int c, const double* alpha, const double* beta
         p->last_launches += sp->last_launches;
         PANEL_CUDA(cudaEventRecord(ev_done[j], st));
         PANEL_CUDA(cudaStreamWaitEvent(cout, ev_done[j], 0));
-        if (c_len) PANEL_CUDA(cudaMemcpyAsync(hC + c_off * es, dC, static_cast<size_t>(c_len) * es, cudaMemcpyDeviceToHost, cout));
+        for (const auto& pc : cpieces)
+            PANEL_CUDA(cudaMemcpyAsync(hC + pc.src_off * es, dC + pc.dst_off * es, static_cast<size_t>(pc.len) * es, cudaMemcpyDeviceToHost, cout));
         PANEL_CUDA(cudaEventRecord(ev_out[j], cout));
     }
     // the caller's stream completes only when the last panel is back on the host
@@ -577,19 +574,23 @@ int cosma_b200_plan_local_blocks(void* plan, int matrix, int rank, int* out, int
     });
 }
 
-/* Planning only: column panel j of c of this plan's rank (exec_internal.h host_panel_pieces). pieces: (src_off, len, dst_off) triples of
- * local B; the panel of local C is c_len elements from c_off. *eligible = 0 when the layout cannot be cut this way. */
-int cosma_b200_plan_host_panel(void* plan, int c, int j, int64_t* pieces, int cap, int* n_pieces, int64_t* c_off, int64_t* c_len, int* eligible) {
-    if (!plan || !n_pieces || !c_off || !c_len || !eligible) return COSMA_B200_INVALID_ARG;
+/* Planning only: column panel j of c of this plan's rank (exec_internal.h host_panel_pieces). b_pieces / c_pieces: (src_off, len, dst_off)
+ * triples of local B / local C. *eligible = 0 when the layout cannot be cut this way. */
+int cosma_b200_plan_host_panel(void* plan, int c, int j, int64_t* b_pieces, int b_cap, int* n_b, int64_t* c_pieces, int c_cap, int* n_c,
+                               int* eligible) {
+    if (!plan || !n_b || !n_c || !eligible) return COSMA_B200_INVALID_ARG;
     return guarded("cosma_b200_plan_host_panel", [&]() -> int {
         Plan* p = static_cast<Plan*>(plan);
-        std::vector<cosma_b200::PanelPiece> v;
-        *n_pieces = 0; *c_off = 0; *c_len = 0;
-        *eligible = !p->schedule.idle() && cosma_b200::host_panel_pieces(p->schedule, p->schedule.rank(), c, j, v, *c_off, *c_len) ? 1 : 0;
+        std::vector<cosma_b200::PanelPiece> vb, vc;
+        *n_b = 0; *n_c = 0;
+        *eligible = !p->schedule.idle() && cosma_b200::host_panel_pieces(p->schedule, p->schedule.rank(), c, j, vb, vc) ? 1 : 0;
         if (!*eligible) return COSMA_B200_OK;
-        *n_pieces = static_cast<int>(v.size());
-        if (pieces && cap >= 3 * *n_pieces)
-            for (size_t i = 0; i < v.size(); ++i) { pieces[3 * i] = v[i].src_off; pieces[3 * i + 1] = v[i].len; pieces[3 * i + 2] = v[i].dst_off; }
+        *n_b = static_cast<int>(vb.size());
+        *n_c = static_cast<int>(vc.size());
+        if (b_pieces && b_cap >= 3 * *n_b)
+            for (size_t i = 0; i < vb.size(); ++i) { b_pieces[3 * i] = vb[i].src_off; b_pieces[3 * i + 1] = vb[i].len; b_pieces[3 * i + 2] = vb[i].dst_off; }
+        if (c_pieces && c_cap >= 3 * *n_c)
+            for (size_t i = 0; i < vc.size(); ++i) { c_pieces[3 * i] = vc[i].src_off; c_pieces[3 * i + 1] = vc[i].len; c_pieces[3 * i + 2] = vc[i].dst_off; }
         return COSMA_B200_OK;
     });
 }

@@ -140,8 +140,8 @@ def main(argv=None):
             verdicts = []
             for r in range(d["P_used"]):
                 pl = MultiplyPlan(None, a.m, a.n, a.k, a.steps, code, rank=r, nranks=a.P, allocate=False)
-                npc, coff, clen, ok = ctypes.c_int(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
-                pl.lib.cosma_b200_plan_host_panel(pl.handle, c, 0, None, 0, ctypes.byref(npc), ctypes.byref(coff), ctypes.byref(clen), ctypes.byref(ok))
+                nb, nc, ok = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+                pl.lib.cosma_b200_plan_host_panel(pl.handle, c, 0, None, 0, ctypes.byref(nb), None, 0, ctypes.byref(nc), ctypes.byref(ok))
                 n_gemm = sum(op["kind"] == "gemm" for op in pl.ops())
                 verdicts.append(bool(ok.value) and n_gemm == 1)
                 pl.destroy()

@@ -117,13 +117,14 @@ COSMA_B200_API int cosma_b200_plan_local_blocks(void* plan, int matrix, int rank
  * Asynchronous on `stream`. Idle ranks return immediately. */
 COSMA_B200_API int cosma_b200_multiply(void* plan, const double* alpha, const double* beta, void* A, void* B, void* C,
                                        void* stream);
-/* Planning only (host-resident operands at N > 1): column panel j of c of this rank's local matrices. Panel j of all ranks --
- * local C columns [j, j+1) * width/c and, of local B, the j-th c-th of every C column range inside the rank's B columns -- is the
- * native layout of the problem (m, n / c, k) under the same strategy, so the host-pointer entry point can run c sub-problems with A
- * uploaded and gathered once while panel j + 1 travels up and panel j - 1 down (COSMA_B200_HOST_PANELS=c, opt-in). pieces: (src_off,
- * len, dst_off) element triples of local B; *eligible = 0 when the layout cannot be cut this way. */
-COSMA_B200_API int cosma_b200_plan_host_panel(void* plan, int c, int j, int64_t* pieces, int cap, int* n_pieces, int64_t* c_off, int64_t* c_len,
-                                              int* eligible);
+/* Planning only (host-resident operands at N > 1): column panel j of c of this rank's local matrices. The column ranges
+ * of all ranks' B and C blocks are refined into elementary ranges; panel j of all ranks -- the j-th c-th of every elementary range,
+ * taken from local B where it lies inside the rank's B columns and from local C where inside its C columns -- is the native layout of
+ * the problem (m, n / c, k) under the same strategy, so the host-pointer entry point can run c sub-problems with A uploaded and
+ * gathered once while panel j + 1 travels up and panel j - 1 down (COSMA_B200_HOST_PANELS=c, opt-in). b_pieces / c_pieces: (src_off,
+ * len, dst_off) element triples (local buffer -> panel buffer); *eligible = 0 when the layout cannot be cut this way. */
+COSMA_B200_API int cosma_b200_plan_host_panel(void* plan, int c, int j, int64_t* b_pieces, int b_cap, int* n_b, int64_t* c_pieces, int c_cap,
+                                              int* n_c, int* eligible);
 /* Same with HOST local matrices (pinned for asynchrony): H2D of local A, B (C too when beta != 0) into arenas owned by
  * the plan, run, D2H of local C. The reference's calling convention (host-resident CosmaMatrix buffers). */
 COSMA_B200_API int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta, const void* A, const void* B,

@@ -158,6 +158,7 @@ def _run_world_short(world, cases, env, limit=150):
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,cases", [
     (2, [(1000, 2048, 64, "pn2", "d", 1.0, 0.0, "host"), (1000, 2048, 64, "pn2", "d", 2.0, 1.0, "host"), (512, 1536, 96, "pn2", "z", 1.0, 0.0, "host"),
+         (1800, 4096, 64, "pm2", "z", 1.0, 0.5, "host"),                                     # pm2: B is divided more finely than C -> two C pieces per panel
          (1700, 7000, 96, "pk2", "d", 1.0, 1.0, "host")]),                                   # pk2: nothing is gathered -> the plain streamed path
     (4, [(1024, 2048, 512, "pn2,pk2", "d", 1.0, 0.0, "host"), (1024, 2048, 512, "pn2,pk2", "d", 1.0, 1.0, "host")]),
     (8, [(2048, 4096, 2048, "pm2,pn2,pk2", "d", 1.0, 0.0, "host"), (1024, 2048, 1024, "pm2,pn2,pk2", "s", 1.0, 1.0, "host")]),
