@@ -6,6 +6,7 @@ reference's order), costa::transform on the device, multiply_using_layout and p?
 Mirrors the reference's tests/pdgemm.cpp (descriptor cases incl. sub-matrices, transposes, NaN-filled C with beta = 0),
 tests/multiply_using_layout.cpp and libs/COSTA/tests/unit/test_utils.cpp."""
 import os
+import time
 import socket
 import sys
 
@@ -408,9 +409,15 @@ def _run_world(world, nprow, npcol):
     procs = [ctx.Process(target=_worker, args=(r, world, port, nprow, npcol, q)) for r in range(world)]
     for p in procs:
         p.start()
+    # one wall-clock limit for the whole world: a rank stuck in a collective must cost minutes, not the GPU call
+    deadline = time.time() + 300
     for p in procs:
-        p.join(900)
-        assert p.exitcode == 0
+        p.join(max(1.0, deadline - time.time()))
+    hung = [p for p in procs if p.is_alive()]
+    for p in hung:
+        p.terminate()
+    assert not hung, "ranks still running after the time limit"
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert q.get(timeout=10)
 
 

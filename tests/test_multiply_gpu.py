@@ -4,6 +4,7 @@ Mirrors the reference's distributed test harness (utils/cosma_utils.hpp:226-283)
 matrices via the Mapper layout, multiply, gather C via the layout, compare with a dense product from the oracle.
 Integer-valued inputs -> the comparison is bit-exact (reduction order cannot matter)."""
 import os
+import time
 import socket
 import sys
 
@@ -191,9 +192,15 @@ def _run_world(world, cases):
     procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
     for p in procs:
         p.start()
+    # one wall-clock limit for the whole world: a rank stuck in a collective must cost minutes, not the GPU call
+    deadline = time.time() + 300
     for p in procs:
-        p.join(600)
-        assert p.exitcode == 0
+        p.join(max(1.0, deadline - time.time()))
+    hung = [p for p in procs if p.is_alive()]
+    for p in hung:
+        p.terminate()
+    assert not hung, "ranks still running after the time limit"
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     res = q.get(timeout=10)
     assert all(res), res
 
