@@ -88,7 +88,8 @@ struct TransformPlan {
     RelayoutBatch stage1;  // pack + local pieces
     RelayoutBatch stage2;  // unpack pieces
     int last_launches = 0;
-    bool materialised = false;  // device buffers allocated and piece lists uploaded
+    bool materialised = false;  // device buffers allocated and piece lists uploaded (all of them)
+    int failed = COSMA_B200_OK;  // status of a materialisation that failed: the plan is dead
     HostMirror mirror;          // device copies of the layout blocks that live in host memory (none: inactive)
     ~TransformPlan();
 };

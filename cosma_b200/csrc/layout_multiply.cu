@@ -366,16 +366,27 @@ int layout_multiply(Comm* c, char dtype, char ta, char tb, int m, int n, int k, 
     st->last_elements[2] = entry->out->host.local_elements;
     st->last_elements[3] = entry->out->host.remote_elements;
 
+    // a transform plan that fails to run (typically: out of device memory while materialising) must not stay in the cache, or the
+    // next call with the same layouts would find it and skip the work
+    auto drop_entry = [&](int status) {
+        cudaStreamSynchronize(stream);
+        for (size_t i = 0; i < st->transforms.size(); ++i)
+            if (&st->transforms[i] == entry) {
+                st->transforms.erase(st->transforms.begin() + i);
+                break;
+            }
+        return status;
+    };
     COSMA_B200_CUDA_TRY(cudaEventRecord(st->ev[0], stream));
     rc = transform_plan_run(*entry->in, stream);
-    if (rc != COSMA_B200_OK) return rc;
+    if (rc != COSMA_B200_OK) return drop_entry(rc);
     COSMA_B200_CUDA_TRY(cudaEventRecord(st->ev[1], stream));
     const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
     rc = cosma_b200_multiply(st->plan, one, zero, st->arena[0], st->arena[1], st->arena[2], stream);
     if (rc != COSMA_B200_OK) return rc;
     COSMA_B200_CUDA_TRY(cudaEventRecord(st->ev[2], stream));
     rc = transform_plan_run(*entry->out, stream);
-    if (rc != COSMA_B200_OK) return rc;
+    if (rc != COSMA_B200_OK) return drop_entry(rc);
     COSMA_B200_CUDA_TRY(cudaEventRecord(st->ev[3], stream));
     st->last_launches = entry->in->last_launches + entry->out->last_launches + cosma_b200_plan_last_launches(st->plan);
     if (launches) *launches = st->last_launches;
@@ -685,7 +696,15 @@ static int xptransform(Grid* ga, Grid* gc, char dtype, char op, int m, int n, co
         }
         entry->stamp = ++gc->clock;
         int rc = transform_plan_run(*entry->plan, stream);
-        if (rc != COSMA_B200_OK) return rc;
+        if (rc != COSMA_B200_OK) {  // never keep a plan that failed (see layout_multiply)
+            cudaStreamSynchronize(stream);
+            for (size_t i = 0; i < gc->transforms.size(); ++i)
+                if (&gc->transforms[i] == entry) {
+                    gc->transforms.erase(gc->transforms.begin() + i);
+                    break;
+                }
+            return rc;
+        }
         gc->last_launches = entry->plan->last_launches;
         if (staged[1]) {
             int myrow = 0, mycol = 0;

@@ -56,9 +56,7 @@ int transform_plan_build(Comm* comm, int rank, int nranks, char dtype, const std
 
 namespace {
 // device side of a plan: buffers + uploaded piece lists (separate from planning so tests can plan without a GPU)
-int materialise(TransformPlan& tp) {
-    if (tp.materialised) return COSMA_B200_OK;
-    tp.materialised = true;
+int materialise_unchecked(TransformPlan& tp) {
     auto& h = tp.host;
     int ms = tp.mirror.build();
     if (ms != COSMA_B200_OK) return ms;
@@ -82,6 +80,30 @@ int materialise(TransformPlan& tp) {
     if (st != COSMA_B200_OK) return st;
     relayout_normalise(h.unpack, tp.recv_buf, nullptr, h.elem_bytes, h.specs, l2);
     return relayout_upload(l2, tp.stage2);
+}
+
+// A plan counts as materialised only once EVERY allocation and upload has succeeded. A plan whose materialisation failed (out of
+// device memory, ...) is dead: its partial device state is released, and every later run reports the failure again instead of
+// launching empty batches (the piece lists were possibly already rewritten to mirror addresses, so a retry cannot be trusted);
+// owners of plan caches drop such plans (layout_multiply.cu).
+int materialise(TransformPlan& tp) {
+    if (tp.materialised) return COSMA_B200_OK;
+    if (tp.failed != COSMA_B200_OK) {
+        set_last_error("transform: this plan could not be materialised on the device earlier (status " + std::to_string(tp.failed) + "); destroy it");
+        return tp.failed;
+    }
+    const int st = materialise_unchecked(tp);
+    if (st == COSMA_B200_OK) {
+        tp.materialised = true;
+        return st;
+    }
+    tp.failed = st;
+    (void)cudaGetLastError();  // a failed cudaMalloc leaves a sticky-until-read error behind
+    relayout_free(tp.stage1);
+    relayout_free(tp.stage2);
+    if (tp.send_buf) { cudaFree(tp.send_buf); tp.send_buf = nullptr; }
+    if (tp.recv_buf) { cudaFree(tp.recv_buf); tp.recv_buf = nullptr; }
+    return st;
 }
 }  // namespace
 

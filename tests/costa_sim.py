@@ -115,10 +115,10 @@ class BlockCyclic:
     """A ScaLAPACK 2D block-cyclic matrix: per-rank local arrays (column-major, leading dimension lld) and the
     global <-> local maps, built from the layout formulas that test_costa_cpu.py pins against the reference."""
 
-    def __init__(self, M, N, mb, nb, nprow, npcol, order="R", rsrc=0, csrc=0, lld_pad=0):
+    def __init__(self, M, N, mb, nb, nprow, npcol, order="R", rsrc=0, csrc=0, lld_pad=0, lld=None):
         self.M, self.N, self.mb, self.nb = M, N, mb, nb
         self.nprow, self.npcol, self.order, self.rsrc, self.csrc = nprow, npcol, order, rsrc, csrc
-        self.lld_pad = lld_pad
+        self.lld_pad, self.lld = lld_pad, lld  # lld: the caller's leading dimension (at least the local row count), else rows + pad
 
     def coords(self, rank):
         if self.order == "C":
@@ -129,6 +129,8 @@ class BlockCyclic:
         pr, pc = self.coords(rank)
         lr = costa.numroc(self.M, self.mb, pr, self.rsrc, self.nprow)
         lc = costa.numroc(self.N, self.nb, pc, self.csrc, self.npcol)
+        if self.lld is not None:
+            return max(self.lld, lr, 1), lc
         return max(lr, 1) + self.lld_pad, lc  # (lld, local columns)
 
     def desc(self, rank):

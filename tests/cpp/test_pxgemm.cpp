@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <fstream>
 #include <limits>
+#include <string>
+#include <unistd.h>
 
 using testutil::real_of;
 extern "C" {
@@ -25,6 +27,13 @@ int numroc_(const int* n, const int* nb, const int* iproc, const int* isrcproc, 
 template <typename T> T gen(int which, int i, int j) { return static_cast<T>(std::sin(0.3 * which + 0.37 * i + 1.1 * j)); }
 template <> std::complex<double> gen<std::complex<double>>(int which, int i, int j) { return {std::sin(0.3 * which + 0.37 * i + 1.1 * j), std::cos(0.7 * which + 0.2 * i - 0.9 * j)}; }
 template <> std::complex<float> gen<std::complex<float>>(int which, int i, int j) { return std::complex<float>(gen<std::complex<double>>(which, i, j)); }
+template <typename T> struct wide_of { using type = double; };
+template <typename T> struct wide_of<std::complex<T>> { using type = std::complex<double>; };
+template <typename T> const char* type_name();
+template <> const char* type_name<float>() { return "float"; }
+template <> const char* type_name<double>() { return "double"; }
+template <> const char* type_name<std::complex<float>>() { return "complex<float>"; }
+template <> const char* type_name<std::complex<double>>() { return "complex<double>"; }
 template <typename T> T conj_if(const T& v, bool) { return v; }
 template <typename T> std::complex<T> conj_if(const std::complex<T>& v, bool c) { return c ? std::conj(v) : v; }
 
@@ -117,39 +126,62 @@ static void run_case(int ctxt, const full_case& pc, int variant) {
         B.fill(myrow, mycol, nprow, npcol, [](int i, int j) { return gen<T>(1, i, j); });
         C.fill(myrow, mycol, nprow, npcol, [&](int i, int j) { return (pc.beta == 0.0 && in_sub_c(i, j)) ? nan : gen<T>(2, i, j); });
     }
-    // dense expectation of sub(C)
-    std::vector<T> dA(static_cast<size_t>(pc.m) * std::max(pc.k, 1)), dB(static_cast<size_t>(std::max(pc.k, 1)) * pc.n), dC(static_cast<size_t>(pc.m) * pc.n);
+    // dense expectation of sub(C), evaluated in DOUBLE precision whatever T is (a 4-byte naive loop is itself off by ~k*eps, more than
+    // the library under test), together with the magnitude sum_l |a_il||b_lj| that bounds the rounding error of any summation order
+    using D = typename wide_of<T>::type;
+    const D alpha_d = static_cast<D>(alpha), beta_d = static_cast<D>(beta);
+    std::vector<D> dA(static_cast<size_t>(pc.m) * std::max(pc.k, 1)), dB(static_cast<size_t>(std::max(pc.k, 1)) * pc.n), dC(static_cast<size_t>(pc.m) * pc.n);
+    std::vector<double> bound(static_cast<size_t>(pc.m) * pc.n, 0.0);
     for (int j = 0; j < pc.k; ++j)
         for (int i = 0; i < pc.m; ++i)
-            dA[static_cast<size_t>(j) * pc.m + i] = tA ? conj_if(gen<T>(0, pc.ia - 1 + j, pc.ja - 1 + i), pc.ta == 'C') : gen<T>(0, pc.ia - 1 + i, pc.ja - 1 + j);
+            dA[static_cast<size_t>(j) * pc.m + i] = static_cast<D>(tA ? conj_if(gen<T>(0, pc.ia - 1 + j, pc.ja - 1 + i), pc.ta == 'C') : gen<T>(0, pc.ia - 1 + i, pc.ja - 1 + j));
     for (int j = 0; j < pc.n; ++j)
         for (int i = 0; i < pc.k; ++i)
-            dB[static_cast<size_t>(j) * pc.k + i] = tB ? conj_if(gen<T>(1, pc.ib - 1 + j, pc.jb - 1 + i), pc.tb == 'C') : gen<T>(1, pc.ib - 1 + i, pc.jb - 1 + j);
+            dB[static_cast<size_t>(j) * pc.k + i] = static_cast<D>(tB ? conj_if(gen<T>(1, pc.ib - 1 + j, pc.jb - 1 + i), pc.tb == 'C') : gen<T>(1, pc.ib - 1 + i, pc.jb - 1 + j));
     for (int j = 0; j < pc.n; ++j)
-        for (int i = 0; i < pc.m; ++i) dC[static_cast<size_t>(j) * pc.m + i] = pc.beta == 0.0 ? T{0} : gen<T>(2, pc.ic - 1 + i, pc.jc - 1 + j);
-    if (pc.k > 0 && pc.alpha != 0.0)
-        testutil::naive_gemm('N', 'N', pc.m, pc.n, pc.k, alpha, dA.data(), pc.m, dB.data(), pc.k, beta, dC.data(), pc.m);
-    else
-        for (auto& v : dC) v = beta * v;
+        for (int i = 0; i < pc.m; ++i) {
+            const D c0 = pc.beta == 0.0 ? D{0} : static_cast<D>(gen<T>(2, pc.ic - 1 + i, pc.jc - 1 + j));
+            D acc{0};
+            double mag = 0.0;
+            if (pc.alpha != 0.0)
+                for (int l = 0; l < pc.k; ++l) {
+                    const D a = dA[static_cast<size_t>(l) * pc.m + i], b = dB[static_cast<size_t>(j) * pc.k + l];
+                    acc += a * b;
+                    mag += std::abs(a) * std::abs(b);
+                }
+            dC[static_cast<size_t>(j) * pc.m + i] = alpha_d * acc + beta_d * c0;
+            bound[static_cast<size_t>(j) * pc.m + i] = std::abs(alpha_d) * mag + std::abs(beta_d) * std::abs(c0);
+        }
 
     entry<T>::get(variant)(&pc.ta, &pc.tb, &pc.m, &pc.n, &pc.k, reinterpret_cast<const R*>(&alpha), reinterpret_cast<const R*>(A.local.data()), &pc.ia, &pc.ja,
                            A.desc, reinterpret_cast<const R*>(B.local.data()), &pc.ib, &pc.jb, B.desc, reinterpret_cast<const R*>(&beta),
                            reinterpret_cast<R*>(C.local.data()), &pc.ic, &pc.jc, C.desc);
 
     bool ok = true, untouched = true, pad = true;
-    const double tol = (sizeof(R) == 4 ? 2e-4 : 1e-11) * std::max(1.0, pc.k / 256.0);  // entries are O(1): errors grow with k
+    double worst = 0.0;
+    // component-wise: |got - want| <= c * (|alpha| sum|a||b| + |beta||c|), c = 2e-6 for 4-byte reals (3xTF32 split: ~2^-21 per product
+    // plus the result's own rounding), 1e-13 for 8-byte ones (north_star's tolerances, stated per element instead of per norm)
+    const double rel = sizeof(R) == 4 ? 2e-6 : 1e-13;
     if (myrow >= 0) {
         for (int lj = 0; lj < C.lcols; ++lj) {
             for (int li = 0; li < C.lld; ++li) {
                 const T got = C.local[static_cast<size_t>(lj) * C.lld + li];
                 if (li >= C.lrows) { pad = pad && got == T{-555}; continue; }
                 const int gi = dist_matrix<T>::l2g(li, C.mb, myrow, C.rsrc, nprow), gj = dist_matrix<T>::l2g(lj, C.nb, mycol, C.csrc, npcol);
-                if (in_sub_c(gi, gj)) ok = ok && std::abs(got - dC[static_cast<size_t>(gj - pc.jc + 1) * pc.m + (gi - pc.ic + 1)]) <= tol;
+                if (in_sub_c(gi, gj)) {
+                    const size_t at = static_cast<size_t>(gj - pc.jc + 1) * pc.m + (gi - pc.ic + 1);
+                    const double err = std::abs(static_cast<D>(got) - dC[at]), tol = rel * bound[at] + std::numeric_limits<R>::min();
+                    if (!(err <= tol)) {
+                        ok = false;
+                        worst = std::max(worst, bound[at] > 0 ? err / bound[at] : err);
+                    }
+                }
                 else untouched = untouched && got == gen<T>(2, gi, gj);
             }
         }
     }
-    CHECK_MSG(ok, "p?gemm " << pc.ta << pc.tb << " " << pc.m << "x" << pc.n << "x" << pc.k << " variant " << variant);
+    CHECK_MSG(ok, "p?gemm " << type_name<T>() << " " << pc.ta << pc.tb << " " << pc.m << "x" << pc.n << "x" << pc.k << " variant " << variant << " grid " << nprow << "x" << npcol
+                            << " worst err/bound " << worst << " (allowed " << rel << ")");
     CHECK_TRUE(untouched);
     CHECK_TRUE(pad);
 }
@@ -192,7 +224,18 @@ int main(int argc, char** argv) {
     // it names, made of the first p_rows x p_cols ranks of the job; sets needing more ranks than the job has are skipped
     {
         const char* env = std::getenv("COSMA_B200_PDGEMM_CASES");
-        std::ifstream in(env && *env ? env : "tests/golden/pdgemm_cases.txt");
+        // the fixture is found relative to this BINARY (tests/cpp/bin/ -> tests/golden/), not to the working directory
+        std::string fixture = env && *env ? env : "";
+        if (fixture.empty()) {
+            char self[4096];
+            const ssize_t len = ::readlink("/proc/self/exe", self, sizeof(self) - 1);
+            std::string dir = len > 0 ? std::string(self, static_cast<size_t>(len)) : std::string(argv[0]);
+            const size_t slash = dir.rfind('/');
+            dir = slash == std::string::npos ? "." : dir.substr(0, slash);
+            fixture = dir + "/../../golden/pdgemm_cases.txt";
+        }
+        std::ifstream in(fixture);
+        CHECK_MSG(in.good(), "cannot open the reference parameter sets: " << fixture);
         full_case fc;
         int v = 0, ran = 0;
         while (in >> fc.ma >> fc.na >> fc.mb >> fc.nb >> fc.mc >> fc.nc >> fc.bma >> fc.bna >> fc.bmb >> fc.bnb >> fc.bmc >> fc.bnc >> fc.ia >> fc.ja >>
@@ -209,6 +252,7 @@ int main(int argc, char** argv) {
             cosma::blacs::Cblacs_gridexit(ctxt);
             ++ran;
         }
+        CHECK_MSG(v == 50, "expected the reference's 50 parameter sets in " << fixture << ", read " << v);
         if (rank == 0) std::printf("reference pdgemm parameter sets: %d read, %d run on %d rank(s)\n", v, ran, P);
     }
     cosma::b200::release_all_comms();

@@ -213,6 +213,70 @@ def test_single_gpu_pxgemm(lib, dtype, host_pointers):
     grid.destroy(); comm.destroy()
 
 
+def _reference_sets(max_ranks):
+    """The reference's own p?gemm parameter sets (tests/pdgemm.cpp via tests/golden/pdgemm_cases.json) that fit max_ranks ranks."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pdgemm_cases.json")) as f:
+        return [c for c in json.load(f)["cases"] if c["p_rows"] * c["p_cols"] <= max_ranks]
+
+
+def _reference_set_case(comm, c, dtype, host_pointers, gather):
+    """One parameter set of the reference's tests/pdgemm.cpp through the C ABI, every argument as the set names it (global sizes, block
+    sizes, sub-matrix origins, rsrc/csrc per matrix, lld = the set's own -- mostly exactly the local row count, i.e. ODD pitches).
+    Integer-valued operands: the dense product is exact in every type; sub(C) holds NaN when beta == 0 (pxgemm_utils.hpp:603-637)."""
+    rank = comm.rank
+    nprow, npcol, order = c["p_rows"], c["p_cols"], c["order"]
+    P = nprow * npcol
+    m, n, k, ta, tb, alpha, beta = c["m"], c["n"], c["k"], c["ta"], c["tb"], c["alpha"], c["beta"]
+    (ia, ja), (ib, jb), (ic, jc) = (c["ia"], c["ja"]), (c["ib"], c["jb"]), (c["ic"], c["jc"])
+    shapes = [(c["ma"], c["na"]), (c["mb"], c["nb"]), (c["mc"], c["nc"])]
+    blks = [(c["bma"], c["bna"]), (c["bmb"], c["bnb"]), (c["bmc"], c["bnc"])]
+    srcs = [(c["src_ma"], c["src_na"]), (c["src_mb"], c["src_nb"]), (c["src_mc"], c["src_nc"])]
+    llds = [c["lld_a"], c["lld_b"], c["lld_c"]]
+    am, an = (m, k) if ta == "N" else (k, m)
+    bm, bn = (k, n) if tb == "N" else (n, k)
+    rng = np.random.default_rng(m * 31 + n * 17 + k)  # same on every rank
+    G = [sim.random_values(rng, s, dtype) for s in shapes]
+    grid = costa.Grid(comm, order, nprow, npcol)
+    bc = [sim.BlockCyclic(s[0], s[1], blk[0], blk[1], nprow, npcol, order, src[0], src[1], lld=(lld if lld > 0 else None))
+          for s, blk, src, lld in zip(shapes, blks, srcs, llds)]
+    Cin = G[2].copy()
+    if beta == 0.0:
+        Cin[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = np.nan
+    locs = [bc[0].scatter(G[0], rank), bc[1].scatter(G[1], rank), bc[2].scatter(Cin, rank)]
+    bufs = [torch.from_numpy(l).pin_memory() for l in locs] if host_pointers else [_dev(l) for l in locs]
+    costa.pxgemm(grid, dtype, ta, tb, m, n, k, alpha, bufs[0].data_ptr(), ia, ja, bc[0].desc(rank), bufs[1].data_ptr(), ib, jb, bc[1].desc(rank),
+                 beta, bufs[2].data_ptr(), ic, jc, bc[2].desc(rank))
+    torch.cuda.synchronize()
+    all_c = gather(bufs[2].cpu().numpy())
+    grid.destroy()
+    if rank != 0:
+        return True
+    got = np.zeros_like(G[2])
+    for r in range(P):
+        bc[2].gather_into(got, all_c[r], r)
+    wide = np.complex128 if dtype in "zc" else np.float64
+    As = sim.apply_op(G[0][ia - 1:ia - 1 + am, ja - 1:ja - 1 + an], ta).astype(wide)
+    Bs = sim.apply_op(G[1][ib - 1:ib - 1 + bm, jb - 1:jb - 1 + bn], tb).astype(wide)
+    want = G[2].copy()
+    want[ic - 1:ic - 1 + m, jc - 1:jc - 1 + n] = np.asarray(alpha * (As @ Bs) + (beta * G[2][ic - 1:ic - 1 + m, jc - 1:jc - 1 + n].astype(wide) if beta != 0.0 else 0)).astype(want.dtype)
+    return bool(np.array_equal(got, want))
+
+
+@pytest.mark.parametrize("dtype", ["d", "z", "s", "c"])
+@pytest.mark.parametrize("host_pointers", [False, True])
+def test_single_gpu_pxgemm_reference_sets(lib, dtype, host_pointers):
+    """The seven P = 1 sets of the reference's tests/pdgemm.cpp below the C++ layer: odd sizes (83 / 77 / 13 / 11 / 7 / 3) with lld == local
+    rows -- the operands TMA cannot address -- and 128 x 128 x 1280 'T','N'."""
+    from cosma_b200.distributed import init_comm
+    comm = init_comm()
+    sets = _reference_sets(1)
+    assert len(sets) == 7
+    for c in sets:
+        assert _reference_set_case(comm, c, dtype, host_pointers, lambda loc: [loc]), c
+    comm.destroy()
+
+
 TRAN_CASES = [
     dict(m=40, n=56, ba=(8, 8), bc=(8, 8), sa=(1, 1), sc=(1, 1), extra=0, alpha=1.0, beta=0.0),
     dict(m=37, n=53, ba=(5, 7), bc=(4, 9), sa=(3, 2), sc=(2, 6), extra=11, alpha=2.0, beta=-1.0),
@@ -328,6 +392,11 @@ def _worker(rank, world, port, nprow, npcol, q):
                 for case in PX_CASES:
                     ok.append(_pxgemm_case(comm, grid, case, dtype, nprow, npcol, order, host, gather))
         grid.destroy()
+    # (2b) the reference's own parameter sets (tests/pdgemm.cpp) whose grid fits this job, each on the grid it names (the first
+    # p_rows x p_cols ranks; the others call with empty local arrays, as ScaLAPACK requires of every process of the context's parent)
+    for c in _reference_sets(world):
+        for dtype, host in (("d", False), ("c", True)):
+            ok.append(_reference_set_case(comm, c, dtype, host, gather))
     # (3) p?tran / p?tranu / p?tranc and p?gemr2d (between a row-major and a column-major numbering of the same grid)
     gr, gc2 = costa.Grid(comm, "R", nprow, npcol), costa.Grid(comm, "C", nprow, npcol)
     for dtype, op in (("d", "T"), ("z", "C"), ("c", "T"), ("s", "N"), ("z", "N")):

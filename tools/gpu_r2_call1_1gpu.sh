@@ -19,6 +19,11 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:rela
     python tools/relayout_bench.py --n 8192 --dtypes z --cases copy --reps 1 >> gpurun_out/ncu_relayout.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm_f64_sm100 -s 2 -c 1 -o gpurun_out/r2_zgemm8192 \
     python tools/gemm_time.py --dtype z --m 8192 --n 8192 --k 8192 --reps 1 > gpurun_out/ncu_zgemm.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32x3 -s 2 -c 1 -o gpurun_out/r2_sgemm8192 \
+    python tools/gemm_time.py --dtype s --m 8192 --n 8192 --k 8192 --reps 1 > gpurun_out/ncu_sgemm.log 2>&1
+for dt in d z s c; do timeout 60 python tools/gemm_time.py --dtype $dt --m 8192 --n 8192 --k 8192 --reps 3 >> gpurun_out/r2_gemm_times.jsonl 2>&1; done
+timeout 60 python tools/gemm_time.py --dtype c --transa C --m 8192 --n 8192 --k 8192 --reps 3 >> gpurun_out/r2_gemm_times.jsonl 2>&1
+timeout 60 python tools/gemm_time.py --dtype z --transa C --m 8192 --n 8192 --k 8192 --reps 3 >> gpurun_out/r2_gemm_times.jsonl 2>&1
 # 4. relayout sweep and the COSTA miniapps from host memory (GB/s of matrix bytes, end to end)
 timeout 200 python tools/relayout_bench.py --n 16384 > gpurun_out/r2_relayout_sweep.txt 2>&1
 # 4b. the shared-memory transpose variant: bit-exact suite under the switch, then the same sweep (transposes only)
