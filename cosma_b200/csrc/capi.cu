@@ -3,6 +3,7 @@
 #include "gemm_f64_sm100.h"
 #include "gemm_tf32x3_sm100.h"
 #include "exec_internal.h"
+#include "cta_budget.h"
 
 #include <string>
 
@@ -14,6 +15,10 @@ thread_local int g_last_launches = 0;
 
 namespace cosma_b200 {
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+int& reserved_sms() {
+    thread_local int r = 0;
+    return r;
+}
 }  // namespace cosma_b200
 
 extern "C" {

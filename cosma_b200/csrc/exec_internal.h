@@ -5,6 +5,7 @@
 #include "relayout_sm100.h"
 #include "host_mirror.h"
 
+#include <cosma/overlap.hpp>
 #include <cosma/schedule.hpp>
 #include <costa/transform_plan.hpp>
 
@@ -42,6 +43,14 @@ struct Plan {
     std::vector<float> gemm_ms;  // optional per-GEMM timing of the last run
     std::vector<cudaEvent_t> ev;
     bool time_gemms = false;
+    // communication / computation overlap (host/overlap.cpp): the micro-op lowering of the schedule's tail. enabled only if EVERY rank of
+    // the strategy lowers (ring mates must agree on the protocol); then the ring communicators are limited to `reserved` CTAs and
+    // narrow GEMMs leave as many SMs free.
+    cosma::OverlapProgram overlap;
+    int reserved = 0;
+    cudaStream_t comm_stream = nullptr;
+    std::vector<cudaEvent_t> micro_ev;  // [2 * micro-op] start / end, + 1 entry event
+    bool last_run_overlapped = false;
     // library-owned device arenas for the host-pointer entry point (allocated on first use)
     char* owned[3] = {nullptr, nullptr, nullptr};
     // column-panel pipelining of the host-pointer entry point (COSMA_B200_HOST_PANELS, multiply_exec.cu): the plan of one panel

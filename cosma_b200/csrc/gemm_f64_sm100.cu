@@ -28,6 +28,7 @@
 #include "sm100_common.cuh"
 #include "gemm_f64_sm100.h"
 #include "repack.h"
+#include "cta_budget.h"
 
 #include <cstdio>
 #include <mutex>
@@ -526,7 +527,7 @@ cudaError_t launch_tma(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
         configured = true;
     }
     const int tiles = p.tiles_m * p.tiles_n;
-    const int grid = tiles < sms ? tiles : sms;
+    const int grid = gemm_grid(tiles, sms);
     kern<<<grid, THREADS, SMEM_BYTES, stream>>>(ma, mb, p);
     return cudaGetLastError();
 }

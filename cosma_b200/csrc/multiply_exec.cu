@@ -9,6 +9,7 @@
 #include "gemm_f64_sm100.h"
 #include "gemm_tf32x3_sm100.h"
 #include "host_stream.h"
+#include "cta_budget.h"
 
 #include <cstring>
 
@@ -33,6 +34,25 @@ __global__ void axpby_kernel(int64_t n, R br, R bi, R* __restrict__ C, const R* 
 
 #define NCCL_TRY COSMA_B200_NCCL_TRY
 #define CUDA_TRY COSMA_B200_CUDA_TRY
+
+// C[i] = (br, bi) * C[i] + T[i] over n elements of the plan's type
+int launch_axpby(const Plan& plan, int64_t n, double br, double bi, char* C, const char* T, cudaStream_t stream) {
+    if (n <= 0) return COSMA_B200_OK;
+    const int threads = 256;
+    int blocks = static_cast<int>(std::min<int64_t>((n + threads - 1) / threads, 148 * 8));
+    if (blocks < 1) blocks = 1;
+    const int E = plan.elem_reals;
+    if (plan.real_bytes == 8) {
+        if (E == 1) axpby_kernel<double, false><<<blocks, threads, 0, stream>>>(n, br, bi, reinterpret_cast<double*>(C), reinterpret_cast<const double*>(T));
+        else axpby_kernel<double, true><<<blocks, threads, 0, stream>>>(n, br, bi, reinterpret_cast<double*>(C), reinterpret_cast<const double*>(T));
+    } else {
+        const float fr = static_cast<float>(br), fi = static_cast<float>(bi);
+        if (E == 1) axpby_kernel<float, false><<<blocks, threads, 0, stream>>>(n, fr, fi, reinterpret_cast<float*>(C), reinterpret_cast<const float*>(T));
+        else axpby_kernel<float, true><<<blocks, threads, 0, stream>>>(n, fr, fi, reinterpret_cast<float*>(C), reinterpret_cast<const float*>(T));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return COSMA_B200_OK;
+}
 
 int run_allgather(const Plan& plan, const cosma::ScheduleOp& op, char* arena, cudaStream_t stream) {
     const NcclApi* N = nccl();
@@ -111,20 +131,97 @@ int run_reduce(const Plan& plan, const cosma::ScheduleOp& op, char* arena, const
         NCCL_TRY(N->GroupEnd());
     }
     if (!beta_zero && mine_total > 0) {
-        const int threads = 256;
-        int blocks = static_cast<int>(std::min<int64_t>((mine_total + threads - 1) / threads, 148 * 8));
-        if (blocks < 1) blocks = 1;
-        const int64_t cnt = E == 2 ? mine_total : mine_total;
-        if (plan.real_bytes == 8) {
-            if (E == 1) axpby_kernel<double, false><<<blocks, threads, 0, stream>>>(cnt, br, bi, reinterpret_cast<double*>(dst), reinterpret_cast<const double*>(recv));
-            else axpby_kernel<double, true><<<blocks, threads, 0, stream>>>(cnt, br, bi, reinterpret_cast<double*>(dst), reinterpret_cast<const double*>(recv));
-        } else {
-            const float fr = static_cast<float>(br), fi = static_cast<float>(bi);
-            if (E == 1) axpby_kernel<float, false><<<blocks, threads, 0, stream>>>(cnt, fr, fi, reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(recv));
-            else axpby_kernel<float, true><<<blocks, threads, 0, stream>>>(cnt, fr, fi, reinterpret_cast<float*>(dst), reinterpret_cast<const float*>(recv));
-        }
-        CUDA_TRY(cudaGetLastError());
+        const int st = launch_axpby(plan, mine_total, br, bi, dst, recv, stream);
+        if (st != COSMA_B200_OK) return st;
     }
+    return COSMA_B200_OK;
+}
+
+void beta_of(cosma::BetaMode mode, const double* user, int E, double out[2]) {
+    out[0] = out[1] = 0.0;
+    if (mode == cosma::BetaMode::ONE) out[0] = 1.0;
+    else if (mode == cosma::BetaMode::USER) { out[0] = user[0]; out[1] = E == 2 ? user[1] : 0.0; }
+}
+
+// The overlapped form of a schedule (cosma::OverlapProgram, host/overlap.cpp): micro-ops issued on two streams -- the caller's for the
+// GEMM panels, the plan's own high-priority stream for the NCCL kernels -- tied together by events. Narrow GEMMs leave plan.reserved
+// SMs to the communication kernels, whose communicators are limited to as many CTAs, so neither side ever waits for the other's SMs.
+int plan_run_overlapped(Plan& plan, const double* alpha, const double* beta, char* arenas[3], cudaStream_t stream) {
+    const auto& prog = plan.overlap.ops;
+    const auto& ops = plan.schedule.ops();
+    const NcclApi* N = nccl();
+    const int E = plan.elem_reals;
+    const int64_t EB = plan.elem_bytes();
+    const ncclDataType_t ndt = plan.real_bytes == 8 ? ncclDouble : ncclFloat;
+    if (!plan.comm_stream) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&plan.comm_stream, cudaStreamNonBlocking, hi));
+    }
+    while (plan.micro_ev.size() < 2 * prog.size() + 1) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        plan.micro_ev.push_back(e);
+    }
+    cudaStream_t comm = plan.comm_stream;
+    cudaEvent_t entry = plan.micro_ev[2 * prog.size()];
+    // the communication stream starts after whatever the caller queued (the operands are where they should be)
+    CUDA_TRY(cudaEventRecord(entry, stream));
+    CUDA_TRY(cudaStreamWaitEvent(comm, entry, 0));
+    int last_comm = -1;
+    for (size_t i = 0; i < prog.size(); ++i) {
+        const cosma::MicroOp& o = prog[i];
+        cudaStream_t s = o.stream ? comm : stream;
+        for (int w : o.wait)
+            if (prog[w].stream != o.stream) CUDA_TRY(cudaStreamWaitEvent(s, plan.micro_ev[2 * w + 1], 0));
+        if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.micro_ev[2 * i], s));
+        int st = COSMA_B200_OK;
+        switch (o.kind) {
+            case cosma::MicroKind::GEMM: {
+                double b[2];
+                beta_of(o.beta, beta, E, b);
+                ScopedReservedSms guard(o.narrow ? plan.reserved : 0);
+                int path = 0;
+                st = launch_gemm_nn(plan.dtype, s, o.m, o.n, o.k, alpha, arenas[0] + o.a_off * EB, o.lda, arenas[1] + o.b_off * EB, o.ldb, b,
+                                    arenas[2] + o.c_off * EB, o.ldc, &path);
+                if (path) ++plan.last_launches;
+                break;
+            }
+            case cosma::MicroKind::ALLGATHER:
+                st = run_allgather(plan, ops[o.op], arenas[ops[o.op].matrix], s);
+                break;
+            case cosma::MicroKind::SERIAL: {
+                const auto& op = ops[o.op];
+                if (op.kind == cosma::OpKind::ALLGATHER) st = run_allgather(plan, op, arenas[op.matrix], s);
+                else if (op.kind == cosma::OpKind::REDUCE) st = run_reduce(plan, op, arenas[op.matrix], beta, s);
+                else st = COSMA_B200_INTERNAL_ERROR;  // a program holds exactly one GEMM, lowered into panels
+                break;
+            }
+            case cosma::MicroKind::EXCHANGE: {
+                ncclComm_t ring = plan.ring_comms[o.ring_index];
+                NCCL_TRY(N->GroupStart());
+                NCCL_TRY(N->Send(arenas[2] + o.send_off * EB, static_cast<size_t>(o.count) * E, ndt, o.peer, ring, s));
+                double b[2];
+                beta_of(o.beta, beta, E, b);
+                const int64_t recv_off = (b[0] == 0.0 && b[1] == 0.0) ? o.recv_off_zero : o.recv_off;
+                NCCL_TRY(N->Recv(arenas[2] + recv_off * EB, static_cast<size_t>(o.count) * E, ndt, o.peer, ring, s));
+                NCCL_TRY(N->GroupEnd());
+                break;
+            }
+            case cosma::MicroKind::ACCUMULATE: {
+                double b[2];
+                beta_of(o.beta, beta, E, b);
+                if (o.beta_term && b[0] == 0.0 && b[1] == 0.0) break;  // the exchange landed in C itself
+                st = launch_axpby(plan, o.count, b[0], b[1], arenas[2] + o.dst_off * EB, arenas[2] + o.add_off * EB, s);
+                break;
+            }
+        }
+        if (st != COSMA_B200_OK) return st;
+        CUDA_TRY(cudaEventRecord(plan.micro_ev[2 * i + 1], s));
+        if (o.stream) last_comm = static_cast<int>(i);
+    }
+    // the caller's stream is complete only when the communication stream is
+    if (last_comm >= 0) CUDA_TRY(cudaStreamWaitEvent(stream, plan.micro_ev[2 * last_comm + 1], 0));
     return COSMA_B200_OK;
 }
 
@@ -139,6 +236,11 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
     char* C = static_cast<char*>(C_);
     char* arenas[3] = {A, B, C};
     plan.last_launches = 0;
+    plan.last_run_overlapped = false;
+    if (plan.overlap.enabled && !host && skip_allgather_mask == 0) {
+        plan.last_run_overlapped = true;
+        return plan_run_overlapped(plan, alpha, beta, arenas, stream);
+    }
     // with timing on, every op (GEMM, allgather, reduce) is bracketed by a pair of events: ev[2*i], ev[2*i+1] for op i
     if (plan.time_gemms) {
         while (plan.ev.size() < 2 * plan.schedule.ops().size()) {
@@ -470,8 +572,37 @@ static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int 
         plan->dtype = dtype;
         plan->elem_reals = (dtype == 'z' || dtype == 'c') ? 2 : 1;
         plan->real_bytes = (dtype == 'd' || dtype == 'z') ? 8 : 4;
+        bool use_ring_config = false;
+        // communication / computation overlap: lower the tail of the op list if EVERY active rank's schedule allows it (ring mates must
+        // speak the same protocol; every rank evaluates the same ranks' schedules, so all reach the same verdict)
+        {
+            int sms = 0, dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+            (void)cudaGetLastError();
+            const cosma::OverlapTuning tuning = cosma::overlap_tuning_from_env(dtype, sms);
+            const int Pn = static_cast<int>(strategy.P);
+            bool all = tuning.enabled && Pn > 1 && Pn <= 64;
+            std::string why;
+            for (int r = 0; all && r < Pn; ++r) {
+                cosma::OverlapProgram pr = r == rank ? cosma::plan_overlap(plan->schedule, tuning) : cosma::plan_overlap(cosma::Schedule(strategy, r), tuning);
+                if (!pr.enabled) { all = false; why = "rank " + std::to_string(r) + ": " + pr.why; }
+                if (r == rank) plan->overlap = std::move(pr);
+            }
+            if (all) {
+                plan->reserved = tuning.reserved_sms;  // idle ranks too: they take part in the communicator splits with the same configuration
+            } else {
+                plan->overlap = cosma::OverlapProgram();
+                plan->overlap.why = !why.empty() ? why : (!tuning.enabled ? "switched off (COSMA_OVERLAP_COMM_AND_COMP)" : "not a multi-rank schedule of at most 64 ranks");
+            }
+            use_ring_config = all;
+        }
         if (c && nranks > 1) {
             const auto* N = nccl();
+            // overlapped plans: the ring communicators' kernels are limited to the SMs the narrow GEMMs leave free
+            ncclConfig_t ring_config = NCCL_CONFIG_INITIALIZER;
+            ring_config.minCTAs = 1;
+            ring_config.maxCTAs = std::max(1, plan->reserved);
+            ncclConfig_t* config = use_ring_config ? &ring_config : nullptr;
             // one communicator split per parallel step, called by EVERY rank of the parent communicator in step
             // order (idle ranks and ranks outside a ring pass NCCL_SPLIT_NOCOLOR)
             std::vector<int> par_steps;
@@ -484,9 +615,10 @@ static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int 
                 for (size_t i = 0; i < rings.size(); ++i)
                     if (rings[i].step == s) { color = rings[i].color; key = rings[i].my_pos; idx = static_cast<int>(i); }
                 ncclComm_t sub = nullptr;
-                ncclResult_t r = N->CommSplit(c->comm, color, key, &sub, nullptr);
+                ncclResult_t r = N->CommSplit(c->comm, color, key, &sub, config);
                 if (r != ncclSuccess) {
                     set_last_error(std::string("ncclCommSplit: ") + N->GetErrorString(r));
+                    cosma_b200_plan_destroy(plan.release());  // also destroys the ring communicators split so far
                     return COSMA_B200_NCCL_ERROR;
                 }
                 if (idx >= 0) plan->ring_comms[idx] = sub;
@@ -507,6 +639,8 @@ int cosma_b200_plan_destroy(void* plan) {
         for (auto c : p->ring_comms)
             if (c && nccl()) nccl()->CommDestroy(c);
     for (auto e : p->ev) cudaEventDestroy(e);
+    for (auto e : p->micro_ev) cudaEventDestroy(e);
+    if (p->comm_stream) cudaStreamDestroy(p->comm_stream);
     for (auto& a : p->owned)
         if (a) cudaFree(a);
     for (auto e : p->panel_ev) cudaEventDestroy(e);
@@ -687,10 +821,25 @@ int cosma_b200_plan_time_gemms(void* plan, int enable) {
     static_cast<Plan*>(plan)->time_gemms = enable != 0;
     return COSMA_B200_OK;
 }
-/* after a synchronised run with timing enabled: per-GEMM device milliseconds */
+/* after a synchronised run with timing enabled: per-GEMM device milliseconds (overlapped plans: one entry per GEMM panel) */
 int cosma_b200_plan_gemm_times(void* plan, float* out, int cap, int* n) {
     return guarded("cosma_b200_plan_gemm_times", [&]() -> int {
         Plan* p = static_cast<Plan*>(plan);
+        if (!p || !n) return COSMA_B200_INVALID_ARG;
+        if (p->last_run_overlapped) {
+            const auto& prog = p->overlap.ops;
+            int g = 0;
+            for (const auto& o : prog) g += o.kind == cosma::MicroKind::GEMM;
+            *n = g;
+            if (!p->time_gemms || p->micro_ev.size() < 2 * prog.size()) return COSMA_B200_INVALID_ARG;
+            g = 0;
+            for (size_t i = 0; i < prog.size(); ++i) {
+                if (prog[i].kind != cosma::MicroKind::GEMM) continue;
+                if (g < cap && cudaEventElapsedTime(&out[g], p->micro_ev[2 * i], p->micro_ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+                ++g;
+            }
+            return COSMA_B200_OK;
+        }
         const auto& ops = p->schedule.ops();
         int cnt = 0;
         for (const auto& op : ops) cnt += op.kind == cosma::OpKind::GEMM;
@@ -706,32 +855,75 @@ int cosma_b200_plan_gemm_times(void* plan, float* out, int cap, int* n) {
     });
 }
 
-/* after a synchronised run with timing enabled: for every op of the schedule its kind (0 GEMM, 1 allgather, 2 reduce), device
- * milliseconds, and for collectives the bytes this rank puts on / takes off the wire: (d-1)/d of the gathered (allgather) or
- * reduced (reduce-scatter) buffer, d = ring size -- the "bus bandwidth" convention of SURVEY 8d. */
+/* after a synchronised run with timing enabled: for every op of the schedule its kind (0 GEMM, 1 allgather, 2 reduce / exchange of the
+ * partial C, 3 accumulate), device milliseconds on the stream it ran on, and for collectives the bytes this rank puts on / takes off the
+ * wire: (d-1)/d of the gathered (allgather) or reduced (reduce-scatter) buffer, d = ring size -- the "bus bandwidth" convention of
+ * SURVEY 8d. Overlapped plans report their micro-ops (GEMM panels, allgathers and exchange on the communication stream). */
 int cosma_b200_plan_op_times(void* plan, int* kinds, float* ms, int64_t* wire_bytes, int cap, int* n) {
     return guarded("cosma_b200_plan_op_times", [&]() -> int {
         Plan* p = static_cast<Plan*>(plan);
         if (!p || !n) return COSMA_B200_INVALID_ARG;
         const auto& ops = p->schedule.ops();
+        auto wire_of = [&](const cosma::ScheduleOp& op) {
+            int64_t total = 0, mine = 0;
+            if (op.kind != cosma::OpKind::GEMM) {
+                for (size_t g = 0; g < op.piece.size(); ++g)
+                    for (auto v : op.piece[g]) {
+                        total += v;
+                        if (static_cast<int>(g) == op.my_pos) mine += v;
+                    }
+            }
+            return (total - mine) * p->elem_bytes();
+        };
+        auto kind_of = [](const cosma::ScheduleOp& op) { return op.kind == cosma::OpKind::GEMM ? 0 : (op.kind == cosma::OpKind::ALLGATHER ? 1 : 2); };
+        if (p->last_run_overlapped) {
+            const auto& prog = p->overlap.ops;
+            *n = static_cast<int>(prog.size());
+            if (!p->time_gemms || p->micro_ev.size() < 2 * prog.size()) return COSMA_B200_INVALID_ARG;
+            for (size_t i = 0; i < prog.size() && static_cast<int>(i) < cap; ++i) {
+                const auto& o = prog[i];
+                int kind = 0;
+                int64_t wire = 0;
+                switch (o.kind) {
+                    case cosma::MicroKind::GEMM: kind = 0; break;
+                    case cosma::MicroKind::ALLGATHER:
+                    case cosma::MicroKind::SERIAL: kind = kind_of(ops[o.op]); wire = wire_of(ops[o.op]); break;
+                    case cosma::MicroKind::EXCHANGE: kind = 2; wire = o.count * p->elem_bytes(); break;
+                    case cosma::MicroKind::ACCUMULATE: kind = 3; break;
+                }
+                if (kinds) kinds[i] = kind;
+                if (ms && cudaEventElapsedTime(&ms[i], p->micro_ev[2 * i], p->micro_ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+                if (wire_bytes) wire_bytes[i] = wire;
+            }
+            return COSMA_B200_OK;
+        }
         *n = static_cast<int>(ops.size());
         if (!p->time_gemms || p->ev.size() < 2 * ops.size()) return COSMA_B200_INVALID_ARG;
         for (size_t i = 0; i < ops.size() && static_cast<int>(i) < cap; ++i) {
             const auto& op = ops[i];
-            if (kinds) kinds[i] = op.kind == cosma::OpKind::GEMM ? 0 : (op.kind == cosma::OpKind::ALLGATHER ? 1 : 2);
+            if (kinds) kinds[i] = kind_of(op);
             if (ms && cudaEventElapsedTime(&ms[i], p->ev[2 * i], p->ev[2 * i + 1]) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
-            if (wire_bytes) {
-                int64_t total = 0, mine = 0;
-                if (op.kind != cosma::OpKind::GEMM) {
-                    for (size_t g = 0; g < op.piece.size(); ++g)
-                        for (auto v : op.piece[g]) {
-                            total += v;
-                            if (static_cast<int>(g) == op.my_pos) mine += v;
-                        }
-                }
-                wire_bytes[i] = (total - mine) * p->elem_bytes();
-            }
+            if (wire_bytes) wire_bytes[i] = wire_of(op);
         }
+        return COSMA_B200_OK;
+    });
+}
+
+/* The overlapped form of the plan's schedule (include/cosma/overlap.hpp): *enabled = 0 when the plan runs its ops serially (why: a
+ * one-line reason). buf receives OverlapProgram::serialize(); est_ms = {serial, overlapped, communication} estimates of the planner. */
+int cosma_b200_plan_overlap_export(void* plan, int64_t* buf, int64_t cap, int64_t* len, int* enabled, char* why, int why_len, double* est_ms) {
+    return guarded("cosma_b200_plan_overlap_export", [&]() -> int {
+        Plan* p = static_cast<Plan*>(plan);
+        if (!p || !len || !enabled) return COSMA_B200_INVALID_ARG;
+        *enabled = p->overlap.enabled ? 1 : 0;
+        const auto v = p->overlap.serialize();
+        *len = static_cast<int64_t>(v.size());
+        if (buf && cap >= *len && !v.empty()) std::memcpy(buf, v.data(), v.size() * sizeof(int64_t));
+        if (why && why_len > 0) {
+            std::strncpy(why, p->overlap.why.c_str(), static_cast<size_t>(why_len) - 1);
+            why[why_len - 1] = 0;
+        }
+        if (est_ms) { est_ms[0] = p->overlap.est_serial_ms; est_ms[1] = p->overlap.est_overlap_ms; est_ms[2] = p->overlap.est_comm_ms; }
         return COSMA_B200_OK;
     });
 }

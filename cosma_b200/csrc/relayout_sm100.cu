@@ -312,13 +312,18 @@ __global__ void __launch_bounds__(THREADS, 6) relayout_kernel(const DevPiece* __
 // Tunables (defaults chosen from measurements on B200, profiles/; overridable for experiments):
 //   COSMA_B200_RELAYOUT_LR = 4 | 8 | 16   rows of the lane grid used by transposes
 struct Tuning {
-    bool smem_transpose = false;  // COSMA_B200_RELAYOUT_SMEM=ON: transposes through a shared-memory tile (opt-in until measured)
+    // transposes through a padded shared-memory tile (full-line requests on both global sides) or through registers (lane-grid
+    // shuffle). Measured on B200 (profiles/r2_relayout_sweep*.txt, 16384^2 in 256^2 pieces, fraction of the 6543 GB/s copy peak):
+    //   shared:   z 0.85-0.86   d 0.82   c 0.81   s 0.57          registers:   z 0.67   d 0.73   c 0.76   s 0.73
+    // -> default (-1): shared memory for elements of 8 bytes and more, registers for 4-byte ones. COSMA_B200_RELAYOUT_SMEM=ON|OFF forces one.
+    int smem_transpose = -1;
     int lr_shift = 2;  // 4 x 8 lane grid: 64-byte read runs, 128-byte write runs (best of 4|8|16 on B200, profiles/r1_relayout_sweep.txt)
 };
 const Tuning& tuning() {
     static Tuning t = [] {
         Tuning v;
-        if (const char* e = std::getenv("COSMA_B200_RELAYOUT_SMEM")) v.smem_transpose = e[0] == 'O' && e[1] == 'N';
+        if (const char* e = std::getenv("COSMA_B200_RELAYOUT_SMEM"))
+            if (e[0] == 'O') v.smem_transpose = e[1] == 'N' ? 1 : 0;
         if (const char* e = std::getenv("COSMA_B200_RELAYOUT_LR")) {
             const int lr = std::atoi(e);
             v.lr_shift = lr == 8 ? 3 : lr == 16 ? 4 : lr == 2 ? 1 : 2;
@@ -447,6 +452,7 @@ int launch_class(const DevPiece* pieces, int n_pieces, std::int64_t tiles, const
 template <typename Ops>
 int launch_typed(const RelayoutBatch& b, cudaStream_t stream, int* launches) {
     constexpr int VEC = 16 / static_cast<int>(sizeof(typename Ops::E));
+    const bool smem = tuning().smem_transpose < 0 ? sizeof(typename Ops::E) >= 8 : tuning().smem_transpose == 1;
     for (int c = 0; c < RELAYOUT_CLASSES; ++c) {
         if (b.tiles[c] == 0) continue;
         int st;
@@ -454,11 +460,11 @@ int launch_typed(const RelayoutBatch& b, cudaStream_t stream, int* launches) {
             case 0: st = launch_class<Ops, false, 1>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream); break;
             case 1: st = launch_class<Ops, false, VEC>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream); break;
             case 2:
-                st = tuning().smem_transpose ? launch_class<Ops, true, 1, true>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream)
+                st = smem ? launch_class<Ops, true, 1, true>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream)
                                              : launch_class<Ops, true, 1>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream);
                 break;
             default:
-                st = tuning().smem_transpose ? launch_class<Ops, true, VEC, true>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream)
+                st = smem ? launch_class<Ops, true, VEC, true>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream)
                                              : launch_class<Ops, true, VEC>(b.d_pieces[c], b.n_pieces[c], b.tiles[c], b.d_scalars, stream);
                 break;
         }

@@ -36,6 +36,8 @@ def _declare(lib):
     lib.cosma_b200_plan_last_launches.argtypes = [vp]
     lib.cosma_b200_plan_time_gemms.argtypes = [vp, ci]
     lib.cosma_b200_plan_gemm_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci, ctypes.POINTER(ci)]
+    lib.cosma_b200_plan_overlap_export.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(i64), ctypes.POINTER(ci), ctypes.c_char_p, ci,
+                                                   ctypes.POINTER(ctypes.c_double)]
     lib._dist_declared = True
 
 
@@ -96,6 +98,26 @@ def parse_plan(flat):
     return ops
 
 
+def parse_overlap(flat):
+    """Decodes cosma_b200_plan_overlap_export (include/cosma/overlap.hpp, OverlapProgram::serialize) into a list of dicts."""
+    ops, i = [], 0
+    names = ("gemm", "allgather", "exchange", "accumulate", "serial")
+    while i < len(flat):
+        kind, stream, nw = flat[i:i + 3]; i += 3
+        op = {"kind": names[kind], "stream": stream, "wait": list(flat[i:i + nw])}; i += nw
+        if kind == 0:
+            keys = ("a_off", "b_off", "c_off", "lda", "ldb", "ldc", "m", "n", "k", "beta", "narrow")
+        elif kind in (1, 4):
+            keys = ("op",)
+        elif kind == 2:
+            keys = ("ring_index", "peer", "send_off", "recv_off", "recv_off_zero", "count", "beta")
+        else:
+            keys = ("dst_off", "add_off", "count", "beta", "beta_term")
+        op.update(zip(keys, flat[i:i + len(keys)])); i += len(keys)
+        ops.append(op)
+    return ops
+
+
 class LocalMatrix:
     """One matrix of a plan on this rank: device arena + the view of the rank's local data (CosmaMatrix analogue)."""
 
@@ -144,6 +166,17 @@ class MultiplyPlan:
         buf = (ctypes.c_int64 * max(n.value, 1))()
         self.lib.cosma_b200_plan_export(self.handle, buf, n.value, ctypes.byref(n))
         return parse_plan(list(buf[:n.value]))
+
+    def overlap(self):
+        """-> {"enabled", "why", "ops": micro-ops, "est_ms": (serial, overlapped, communication)}: how the plan overlaps its
+        collectives with the local GEMM (COSMA_OVERLAP_COMM_AND_COMP), see include/cosma/overlap.hpp."""
+        n, en = ctypes.c_int64(0), ctypes.c_int(0)
+        why = ctypes.create_string_buffer(512)
+        est = (ctypes.c_double * 3)()
+        _lib.check(self.lib.cosma_b200_plan_overlap_export(self.handle, None, 0, ctypes.byref(n), ctypes.byref(en), why, 512, est), "cosma_b200_plan_overlap_export")
+        buf = (ctypes.c_int64 * max(n.value, 1))()
+        _lib.check(self.lib.cosma_b200_plan_overlap_export(self.handle, buf, n.value, ctypes.byref(n), ctypes.byref(en), why, 512, est), "cosma_b200_plan_overlap_export")
+        return {"enabled": bool(en.value), "why": why.value.decode(), "ops": parse_overlap(list(buf[:n.value])) if en.value else [], "est_ms": tuple(est)}
 
     def local_blocks(self, label, rank=None):
         """Blocks (row_first,row_last,col_first,col_last) of `rank` (default: this rank) in local-buffer order."""
@@ -201,7 +234,7 @@ class MultiplyPlan:
         self.lib.cosma_b200_plan_op_times.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float),
                                                       ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         _lib.check(self.lib.cosma_b200_plan_op_times(self.handle, kinds, ms, wb, cap, ctypes.byref(n)), "cosma_b200_plan_op_times")
-        names = ("gemm", "allgather", "reduce")
+        names = ("gemm", "allgather", "reduce", "accumulate")
         return [(names[kinds[i]], ms[i], wb[i]) for i in range(min(n.value, cap))]
 
     def destroy(self):

@@ -135,6 +135,12 @@ COSMA_B200_API int cosma_b200_plan_gemm_times(void* plan, float* out_ms, int cap
 /* With timing enabled, per op of the compiled schedule: kind (0 GEMM, 1 allgather, 2 reduce-scatter), device ms, and for the
  * collectives the bytes this rank exchanges, (d-1)/d of the gathered / reduced buffer (ring size d). */
 COSMA_B200_API int cosma_b200_plan_op_times(void* plan, int* kinds, float* ms, int64_t* wire_bytes, int cap, int* n);
+/* The plan's communication / computation overlap (reference one_sided_communicator.cpp:417-1016, gate strategy.cpp:851-901; here a
+ * plan-time lowering, include/cosma/overlap.hpp): *enabled = 0 when the ops run serially (why = a one-line reason; controlled by
+ * COSMA_OVERLAP_COMM_AND_COMP = ON | OFF | FORCE). buf receives the micro-op program, est_ms[3] the planner's estimates
+ * {serial, overlapped, communication}. */
+COSMA_B200_API int cosma_b200_plan_overlap_export(void* plan, int64_t* buf, int64_t cap, int64_t* len, int* enabled, char* why, int why_len,
+                                                  double* est_ms);
 
 /* ---- COSTA relayout (R3/R4 + exchange) ------------------------------------------------------------------
  * Layout description in the shape of the reference's C interface (src/cosma/cinterface.hpp:16-41: struct block,

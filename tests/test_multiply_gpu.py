@@ -131,9 +131,22 @@ def _worker(rank, world, port, cases, q):
     comm = init_comm()
     results = []
     for case in cases:
-        (m, n, k, steps, dtype, alpha, beta), via_host = case[:7], len(case) > 7 and case[7] == "host"
+        (m, n, k, steps, dtype, alpha, beta), tags = case[:7], set(case[7:])
+        via_host = "host" in tags
         Ag, Bg, Cg = _globals(m, n, k, dtype)
+        # "overlap": the communication / computation overlap forced on whatever its estimated gain (the decision is taken at plan
+        # creation); "serial": switched off. Untagged cases take the library's own decision.
+        os.environ.pop("COSMA_OVERLAP_COMM_AND_COMP", None)
+        if "overlap" in tags:
+            os.environ["COSMA_OVERLAP_COMM_AND_COMP"] = "FORCE"
+        elif "serial" in tags:
+            os.environ["COSMA_OVERLAP_COMM_AND_COMP"] = "OFF"
         pl = MultiplyPlan(comm, m, n, k, steps, dtype)
+        os.environ.pop("COSMA_OVERLAP_COMM_AND_COMP", None)
+        if "overlap" in tags and not pl.idle:
+            assert pl.overlap()["enabled"], pl.overlap()["why"]
+        if "serial" in tags:
+            assert not pl.overlap()["enabled"]
         if not pl.idle:
             for label, mat, full in (("A", pl.A, Ag), ("B", pl.B, Bg), ("C", pl.C, Cg)):
                 host = np.zeros(mat.initial, dtype=full.dtype)
@@ -221,6 +234,13 @@ def test_two_gpus(lib):
         (1000, 9000, 64, "pn2", "d", 1.0, 1.0, "host"),
         (1800, 4000, 64, "pm2", "z", 1.0, 0.0, "host"),
         (300, 260, 220, "sm2,pn2,sk3", "d", 2.0, 1.0, "host"),  # several GEMMs: plain up-front copies
+        # communication / computation overlap (COSMA_OVERLAP_COMM_AND_COMP): each split kind on its own
+        (1024, 1024, 1024, "pk2", "d", 1.0, 0.0, "overlap"),    # peer's half of C first, exchanged while the own half is computed
+        (1024, 1024, 1024, "pk2", "d", 2.0, -1.0, "overlap"),   # ... with the staged beta term
+        (1024, 1024, 1024, "pm2", "d", 1.0, 1.0, "overlap"),    # own column block of B first
+        (1024, 1024, 1024, "pn2", "z", 1.0 - 0.5j, 0.5j, "overlap"),  # own k block of A first, the other accumulated
+        (2048, 1024, 512, "pk2", "s", 1.0, 1.0, "overlap"),
+        (1024, 1024, 1024, "pk2", "d", 1.0, 0.0, "serial"),
     ])
 
 
@@ -231,6 +251,10 @@ def test_four_gpus(lib):
         (20, 30, 25, "sm2,sn2,pk2,pm2", "d", 1.0, 1.0),
         (400, 400, 400, "", "z", 1.0, 0.0),
         (512, 512, 512, "pn2,pk2", "s", 1.0, 0.0),
+        (1024, 1024, 1024, "pn2,pk2", "d", 1.0, 0.0, "overlap"),
+        (1024, 2048, 1024, "pm2,pk2", "d", 2.0, 1.0, "overlap"),
+        (1024, 1024, 1024, "pm2,pn2", "z", 1.0, 1.0, "overlap"),
+        (1024, 1024, 1024, "pk2,pk2", "c", 1.0, 0.0, "overlap"),   # inner reduce overlapped, outer one serial
     ])
 
 
@@ -244,4 +268,8 @@ def test_eight_gpus(lib):
         (1000, 1000, 1000, "pm2,pn2,pk2", "z", 1.0, 1.0),
         (1024, 1024, 1024, "pm2,pn2,pk2", "s", 1.0, 0.0),
         (100, 100, 100, "sm2,pn2,sk2,pm2,sn2,pk2", "c", 1.0, 1.0),  # tests/scalar_matmul.cpp, complex<float>
+        (2048, 2048, 2048, "pm2,pn2,pk2", "d", 1.0, 0.0, "overlap"),   # BASELINE configs[2] strategy, both allgathers and the reduce overlapped
+        (2048, 2048, 2048, "pm2,pn2,pk2", "d", 2.0, 1.0, "overlap"),
+        (2048, 1024, 2048, "pn2,pm2,pk2", "z", 1.0, 0.5, "overlap"),
+        (2048, 2048, 1024, "pk2,pm2,pn2", "s", 1.0, 0.0, "overlap"),   # k split first: the reduce still follows the GEMM directly
     ])
