@@ -264,43 +264,78 @@ def gather_local_to_global(plan, label, local, full, rank=None):
     return pos
 
 
-class MultiplyJob:
-    """bench.py's N > 1 workload: one cosma::multiply of (m, n, k) over `world` GPUs with the automatic strategy,
-    synthetic U[0,10) local matrices (the reference miniapp's fill, miniapp/cosma_miniapp.cpp:21-25,64-70)."""
+def _formula(which, rows, cols, cplx):
+    """Integer-valued synthetic operands defined by GLOBAL coordinates, so that any rank can evaluate any element of A (which = 0) or
+    B (which = 1) without communication: values in 0..9 (Tiled-MM's exact-test convention, libs/Tiled-MM/tests/test-multiply.cpp:60-68).
+    rows, cols: int64 tensors that broadcast against each other. -> (re, im) int64 tensors (im = None for real types)."""
+    def f(salt):
+        h = (rows * 1664525 + cols * 1013904223 + (rows ^ cols) * 69069 + salt * 7919) & 0x7FFFFFFF
+        return (h >> 7) % 10
+    return f(which), (f(which + 2) if cplx else None)
 
-    def __init__(self, m, n, k, world, rank, device, steps=""):
+
+class MultiplyJob:
+    """bench.py's workload: one cosma::multiply of (m, n, k) over `world` GPUs (world = 1: a single local GEMM) with the automatic
+    strategy, synthetic U[0,10) local matrices (the reference miniapp's fill, miniapp/cosma_miniapp.cpp:21-25,64-70)."""
+
+    def __init__(self, m, n, k, world, rank, device, steps="", dtype="d", comm=None):
         import torch
-        self.comm = init_comm(device)
-        self.plan = MultiplyPlan(self.comm, m, n, k, steps, "d", device=device)
+        self.own_comm = comm is None
+        self.comm = comm if comm is not None else init_comm(device)
+        self.dtype = dtype
+        self.tdt = {"d": torch.float64, "z": torch.complex128, "s": torch.float32, "c": torch.complex64}[dtype]
+        self.cplx = dtype in "zc"
+        self.plan = MultiplyPlan(self.comm, m, n, k, steps, dtype, device=device)
         self.strategy_string = self.plan.strategy
         gen = torch.Generator(device=device)
         gen.manual_seed(rank)
+        rdt = torch.float64 if dtype in "dz" else torch.float32
         for mat in (self.plan.A, self.plan.B):
             if mat.initial:
-                mat.local.copy_(torch.rand(mat.initial, device=device, dtype=torch.float64, generator=gen) * 10)
+                if self.cplx:
+                    mat.local.copy_(torch.view_as_complex(torch.rand(mat.initial, 2, device=device, dtype=rdt, generator=gen) * 10))
+                else:
+                    mat.local.copy_(torch.rand(mat.initial, device=device, dtype=rdt, generator=gen) * 10)
         self.plan.C.local.fill_(float("nan"))
         self.plan.time_gemms(True)
-        ops = [op for op in self.plan.ops() if op["kind"] == "gemm"]
-        self.flops_per_local_gemm = sum(2.0 * op["m"] * op["n"] * op["k"] for op in ops) / max(len(ops), 1)
-        self.device = device
+        self.flop_factor = 8.0 if self.cplx else 2.0
+        self.device, self.rank, self.world = device, rank, world
 
     def run(self):
         return self.plan.multiply(1.0, 0.0)
+
+    def gemm_launch_stats(self):
+        """(flops of this rank's GEMM launches in the last step, their summed device ms, number of launches)."""
+        t = self.plan.gemm_times_ms()
+        return self.plan.gemm_flops, sum(t), len(t)
 
     def mean_gemm_ms(self):
         t = self.plan.gemm_times_ms()
         return sum(t) / max(len(t), 1)
 
-    def collectives(self):
-        """Device time and bus bandwidth of the collectives of the last step on this rank (bytes = (d-1)/d of the
-        gathered / reduced buffer per rank)."""
+    def collectives(self, step_ms=None):
+        """Device time and bus bandwidth of the collectives of the last step on this rank (bytes = (d-1)/d of the gathered /
+        reduced buffer per rank), and -- given the step's duration -- how much of it the GEMM panels hid (overlapped plans run them on a
+        second stream): exposed = step - (GEMM + accumulate time), hidden = communication time - exposed."""
         out = {}
+        ov = self.plan.overlap()
+        times = self.plan.op_times()
         for kind in ("allgather", "reduce"):
-            sel = [(ms, wb) for k, ms, wb in self.plan.op_times() if k == kind]
+            sel = [(ms, wb) for k, ms, wb in times if k == kind]
             if not sel:
                 continue
             ms, wb = sum(x[0] for x in sel), sum(x[1] for x in sel)
             out[kind] = {"count": len(sel), "ms": ms, "wire_bytes_per_rank": wb, "busbw_GBps": (wb / (ms * 1e-3) * 1e-9) if ms > 0 else None}
+        out["overlapped"] = ov["enabled"]
+        out["overlap_note"] = ov["why"]
+        compute = sum(ms for k, ms, _ in times if k in ("gemm", "accumulate"))
+        comm = sum(ms for k, ms, _ in times if k in ("allgather", "reduce"))
+        out["gemm_launches"] = sum(1 for k, _, _ in times if k == "gemm")
+        out["compute_ms"] = compute
+        if step_ms is not None:
+            exposed = max(0.0, step_ms - compute)
+            out["exposed_ms"] = exposed
+            out["hidden_ms"] = max(0.0, comm - exposed)
         return out
 
     def e2e(self, reps):
@@ -308,19 +343,114 @@ class MultiplyJob:
         import torch
         import torch.distributed as dist
         pl = self.plan
-        hA = torch.empty(max(pl.initial_elements[0], 1), dtype=torch.float64).pin_memory(); hA[:pl.initial_elements[0]].copy_(pl.A.local)
-        hB = torch.empty(max(pl.initial_elements[1], 1), dtype=torch.float64).pin_memory(); hB[:pl.initial_elements[1]].copy_(pl.B.local)
-        hC = torch.empty(max(pl.initial_elements[2], 1), dtype=torch.float64).pin_memory()
-        pl.multiply_host(hA, hB, hC); torch.cuda.synchronize(); dist.barrier()
+        multi = self.world > 1
+        hA = torch.empty(max(pl.initial_elements[0], 1), dtype=self.tdt, pin_memory=True); hA[:pl.initial_elements[0]].copy_(pl.A.local)
+        hB = torch.empty(max(pl.initial_elements[1], 1), dtype=self.tdt, pin_memory=True); hB[:pl.initial_elements[1]].copy_(pl.B.local)
+        hC = torch.empty(max(pl.initial_elements[2], 1), dtype=self.tdt, pin_memory=True)
+        pl.multiply_host(hA, hB, hC); torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             pl.multiply_host(hA, hB, hC)
         e1.record(); torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1) / reps], device=self.device, dtype=torch.float64)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ok = bool(torch.equal(hC[:1024], pl.C.local[:1024].cpu())) if pl.initial_elements[2] else True
-        return {"value": 2.0 * pl.m * pl.n * pl.k / (ms.item() * 1e-3) * 1e-12, "unit": "TFLOP/s",
-                "h2d_bytes_per_step": 8 * (pl.initial_elements[0] + pl.initial_elements[1]), "d2h_bytes_per_step": 8 * pl.initial_elements[2],
+        if multi:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        n_cmp = min(pl.initial_elements[2], 1 << 20)
+        ok = bool(torch.equal(hC[:n_cmp], pl.C.local[:n_cmp].cpu())) if n_cmp else True
+        eb = hA.element_size()
+        return {"value": self.flop_factor * pl.m * pl.n * pl.k / (ms.item() * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                "h2d_bytes_per_step": eb * (pl.initial_elements[0] + pl.initial_elements[1]), "d2h_bytes_per_step": eb * pl.initial_elements[2],
                 "ms_per_step": ms.item(), "api": "cosma_b200_multiply_host (pinned host local A,B -> local C, per rank)",
                 "matches_device_path": ok}
+
+    def parity(self, samples=32):
+        """One extra multiply on integer-valued operands defined by global coordinates (_formula): every rank checks, EXACTLY,
+        (1) `samples` elements of its own part of C against dot products it evaluates itself in int64, and (2) the sum over its
+        whole part of C against the identity sum_ij C_ij = sum_l (sum_i a_il)(sum_j b_lj) -- a checksum of checksums that covers
+        every element the rank owns. The reference's own criterion (utils/cosma_utils.hpp:366-377) compares against a dense naive
+        GEMM on rank 0, which does not exist at these sizes. -> dict for the bench line (ok = all ranks)."""
+        import torch
+        import torch.distributed as dist
+        pl, dev, cplx = self.plan, self.device, self.cplx
+        i64 = torch.int64
+
+        def fill(mat, label, which):
+            pos = 0
+            for (r0, r1, c0, c1) in pl.local_blocks(label):
+                nr = r1 - r0 + 1
+                rows = torch.arange(r0, r1 + 1, device=dev, dtype=i64)[None, :]
+                for cs in range(c0, c1 + 1, 512):                      # column chunks bound the int64 temporaries
+                    ce = min(cs + 512, c1 + 1)
+                    cols = torch.arange(cs, ce, device=dev, dtype=i64)[:, None]
+                    re, im = _formula(which, rows, cols, cplx)         # (columns, rows): column-major order when flattened
+                    cnt = nr * (ce - cs)
+                    dst = mat.local[pos:pos + cnt]
+                    if cplx:
+                        dst.copy_(torch.complex(re.to(dst.real.dtype), im.to(dst.real.dtype)).reshape(-1))
+                    else:
+                        dst.copy_(re.to(dst.dtype).reshape(-1))
+                    pos += cnt
+        ok, checked = True, 0
+        if not pl.idle:
+            fill(pl.A, "A", 0)
+            fill(pl.B, "B", 1)
+            pl.C.local.fill_(float("nan"))
+        pl.multiply(1.0, 0.0)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        k = pl.k
+        if not pl.idle:
+            gen = torch.Generator(); gen.manual_seed(4321 + self.rank)
+            lk = torch.arange(k, device=dev, dtype=i64)
+            pos = 0
+            for (r0, r1, c0, c1) in pl.local_blocks("C"):
+                nr, nc = r1 - r0 + 1, c1 - c0 + 1
+                blk = pl.C.local[pos:pos + nr * nc]
+                pos += nr * nc
+                # (1) sampled elements
+                for _ in range(samples):
+                    li, lj = int(torch.randint(nr, (1,), generator=gen)), int(torch.randint(nc, (1,), generator=gen))
+                    ar, ai = _formula(0, torch.tensor(r0 + li, device=dev, dtype=i64), lk, cplx)
+                    br, bi = _formula(1, lk, torch.tensor(c0 + lj, device=dev, dtype=i64), cplx)
+                    got = blk[lj * nr + li]
+                    if cplx:
+                        want = complex(int((ar * br - ai * bi).sum()), int((ar * bi + ai * br).sum()))
+                        ok = ok and complex(got.item()) == want
+                    else:
+                        ok = ok and float(got.item()) == float(int((ar * br).sum()))
+                    checked += 1
+                # (2) checksum of the whole block
+                rows = torch.arange(r0, r1 + 1, device=dev, dtype=i64)[:, None]
+                cols = torch.arange(c0, c1 + 1, device=dev, dtype=i64)[None, :]
+                tot_re = torch.zeros((), device=dev, dtype=i64); tot_im = torch.zeros((), device=dev, dtype=i64)
+                step = max(1, min(k, (1 << 25) // max(nr, nc)))
+                for l0 in range(0, k, step):
+                    ls = torch.arange(l0, min(l0 + step, k), device=dev, dtype=i64)
+                    ar, ai = _formula(0, rows, ls[None, :], cplx)       # (rows of the block, l)
+                    br, bi = _formula(1, ls[:, None], cols, cplx)       # (l, columns of the block)
+                    sar, sbr = ar.sum(0), br.sum(1)
+                    if cplx:
+                        sai, sbi = ai.sum(0), bi.sum(1)
+                        tot_re += (sar * sbr - sai * sbi).sum(); tot_im += (sar * sbi + sai * sbr).sum()
+                    else:
+                        tot_re += (sar * sbr).sum()
+                if cplx:
+                    ok = ok and int(blk.real.to(torch.float64).to(i64).sum()) == int(tot_re) and int(blk.imag.to(torch.float64).to(i64).sum()) == int(tot_im)
+                else:
+                    ok = ok and bool(torch.isfinite(blk).all()) and int(blk.to(torch.float64).to(i64).sum()) == int(tot_re)
+        flag = torch.tensor([1 if ok else 0, checked], device=dev, dtype=i64)
+        if self.world > 1:
+            ok_all = flag[:1].clone(); dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+            cnt = flag[1:].clone(); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            ok, checked = bool(ok_all.item()), int(cnt.item())
+        return {"ok": bool(ok), "exact": True, "sampled_elements": checked, "block_checksums": "every rank, every element of its C",
+                "how": "integer-valued A, B from global coordinates; int64 dot products and sum_ij C_ij = sum_l (sum_i a_il)(sum_j b_lj)",
+                "overlapped": pl.overlap()["enabled"]}
+
+    def destroy(self):
+        self.plan.destroy()
+        if self.own_comm:
+            self.comm.destroy()

@@ -1,23 +1,43 @@
 #!/bin/bash
-# Round 2, second call (2 GPUs, <= 6 min of box time = 12 GPU-minutes): the multi-rank paths written after the round-1 GPU budget ran
-# out (DESIGN 9 items 1-3 and the copy-engine probe of item 5). EVERY step carries its own short wall-clock limit and the host layer's
-# receive timeout, so that a protocol error costs seconds, not the call.
-#   gpurun --gpus 2 --timeout 400 -- 'bash tools/gpu_r2_call2_2gpu.sh'
+# Round 2, second call (2 GPUs): multi-rank parity at HEAD (multiply incl. the overlapped schedules, COSTA / p?gemm incl. the reference's own
+# parameter sets, live reference, the C++ programs), rank relabelling and COSMA_ADAPT_STRATEGY switched on, host panels, and the N = 2 bench
+# line with the overlap on / off and 4 / 8 / 16 reserved SMs. EVERY step carries its own wall-clock limit.
+#   gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu_r2_call2_2gpu.sh'
 mkdir -p gpurun_out
 export COSMA_B200_PG_RECV_TIMEOUT=40
 nvidia-smi -L > gpurun_out/gpus.txt
-# the established 2-GPU suite first (its "host" cases -- streamed un-gathered operands -- have not run on 2 GPUs since they were written)
-timeout 90 python -m pytest tests/test_multiply_gpu.py -m gpu -q -k two_gpus > gpurun_out/r2_pytest_two_gpus.txt 2>&1; tail -2 gpurun_out/r2_pytest_two_gpus.txt
-COSMA_B200_CPP_MULTIRANK=1 COSMA_B200_TRACE=ON timeout 120 python -m pytest tests/test_z_cpp_api.py -m gpu -q -k "2-" > gpurun_out/r2_pytest_cpp_n2.txt 2>&1
-echo "pytest rc=$?" >> gpurun_out/r2_pytest_cpp_n2.txt; grep -v "^\[cosma rank" gpurun_out/r2_pytest_cpp_n2.txt | tail -8
-COSMA_B200_REORDER_RANKS=ON timeout 90 python -m pytest tests/test_costa_gpu.py -m gpu -q -k two_gpus > gpurun_out/r2_pytest_relabel_n2.txt 2>&1
-echo "pytest rc=$?" >> gpurun_out/r2_pytest_relabel_n2.txt; tail -3 gpurun_out/r2_pytest_relabel_n2.txt
-timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 2 --steps 3 --warmup 3 \
-    > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; tail -c 900 gpurun_out/r2_bench_n2.json
-COSMA_B200_TEST_HOST_PANELS=1 timeout 200 python -m pytest tests/test_zz_optin_gpu.py -m gpu -q -k "host_panels and 2-" > gpurun_out/r2_pytest_host_panels_n2.txt 2>&1
-echo "pytest rc=$?" >> gpurun_out/r2_pytest_host_panels_n2.txt; tail -3 gpurun_out/r2_pytest_host_panels_n2.txt
-timeout 60 python tools/ce_overlap_probe.py > gpurun_out/r2_ce_overlap_probe.json 2>&1; tail -3 gpurun_out/r2_ce_overlap_probe.json
-for app in pxgemr2d_miniapp pxtran_miniapp; do
-  timeout 60 python -m cosma_b200.launch -np 2 tests/cpp/bin/$app -m 16384 -n 16384 --block_a 256,256 --block_c 128,512 -p 1,2 -t zdouble -r 4 >> gpurun_out/r2_costa_miniapps_n2.txt 2>&1
-done
-tail -8 gpurun_out/r2_costa_miniapps_n2.txt
+t() { # $1 = log name, $2 = limit, rest = command
+  log=gpurun_out/$1; lim=$2; shift 2
+  timeout $lim "$@" > $log 2>&1; echo "rc=$?" >> $log; echo "== $log: $(tail -3 $log | tr '\n' ' ' | cut -c1-300)"
+}
+t r2_pytest_multiply_n2.txt 200 python -m pytest tests/test_multiply_gpu.py -m gpu -q -x -k two_gpus
+t r2_pytest_costa_n2.txt 240 python -m pytest tests/test_costa_gpu.py -m gpu -q -x -k two_gpus
+COSMA_B200_REORDER_RANKS=ON t r2_pytest_costa_relabel_n2.txt 240 python -m pytest tests/test_costa_gpu.py -m gpu -q -x -k two_gpus
+COSMA_ADAPT_STRATEGY=ON t r2_pytest_costa_adapt_n2.txt 240 python -m pytest tests/test_costa_gpu.py -m gpu -q -x -k two_gpus
+t r2_pytest_reflive_n2.txt 200 python -m pytest tests/test_ref_live_gpu.py -m gpu -q -x -k two_gpus
+COSMA_B200_CPP_MULTIRANK=1 t r2_pytest_cpp_n2.txt 300 python -m pytest tests/test_z_cpp_api.py -m gpu -q -k "2-"
+COSMA_B200_TEST_HOST_PANELS=1 t r2_pytest_host_panels_n2.txt 200 python -m pytest tests/test_zz_optin_gpu.py -m gpu -q -k "host_panels and 2-"
+bench() { # $1 = tag, rest: env assignments
+  tag=$1; shift
+  env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus 2 --steps 3 --warmup 3 $EXTRA \
+      > gpurun_out/r2_bench_n2_$tag.json 2> gpurun_out/r2_bench_n2_$tag.err
+  python - "$tag" <<'PY'
+import json, sys
+try:
+    d = json.loads([l for l in open("gpurun_out/r2_bench_n2_%s.json" % sys.argv[1]).read().strip().splitlines() if l.startswith("{")][-1])
+    print(sys.argv[1], "value", round(d["value"], 2), "ms", round(d["ms_per_step"], 2), "e2e", d.get("e2e") and round(d["e2e"].get("value", 0), 1), "parity", d.get("parity") and d["parity"].get("ok"), d.get("collectives"))
+except Exception as e:
+    print(sys.argv[1], "no line:", e)
+PY
+}
+EXTRA=""
+bench auto X=1
+EXTRA="--no-e2e --no-parity --no-cpu-baseline"
+bench serial COSMA_OVERLAP_COMM_AND_COMP=OFF
+bench sms4 COSMA_B200_OVERLAP_SMS=4
+bench sms16 COSMA_B200_OVERLAP_SMS=16
+EXTRA="--no-e2e --no-cpu-baseline --strategy pn2"
+bench pn2_auto X=1
+EXTRA="--no-e2e --no-parity --no-cpu-baseline --strategy pn2"
+bench pn2_serial COSMA_OVERLAP_COMM_AND_COMP=OFF
+ls -la gpurun_out | tail -20
