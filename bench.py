@@ -356,6 +356,7 @@ def run_multiply(env, m, n, k, dtype, steps, warmup, strategy="", with_e2e=True,
     job.destroy()
     from cosma_b200 import _lib
     _lib.load().cosma_b200_release_workspace()
+    env.barrier()  # every rank has dropped its mappings of the others' arenas before anybody frees memory
     torch.cuda.empty_cache()
     return out
 

@@ -9,6 +9,7 @@
 #include <cosma/schedule.hpp>
 #include <costa/transform_plan.hpp>
 
+#include <cstdint>
 #include <map>
 #include <new>
 #include <stdexcept>
@@ -32,6 +33,23 @@ struct Comm {
     ~Comm();
 };
 
+// zero-SM peer transport of the overlapped schedules (peer_transport.h / peer_transport.cu)
+struct PeerLink {
+    int micro = -1;               // index of the micro-op (ALLGATHER or EXCHANGE) in Plan::overlap.ops
+    char* landing[2] = {nullptr, nullptr};  // where to write in the mate's arena (mapped); [1]: the exchange's beta == 0 alternative
+    uint32_t* mate_flags = nullptr;         // the mate's flag pair for this op (mapped): [0] ENTERED, [1] ARRIVED
+    uint32_t* my_flags = nullptr;           // this rank's flag pair for this op
+};
+
+struct PeerTransport {
+    bool ready = false;
+    void* bound[3] = {nullptr, nullptr, nullptr};  // the arenas the landing zones were exchanged for
+    char* flag_block = nullptr;   // own allocation (2 MiB: one IPC allocation of its own): flags at the front, epoch scratch behind
+    std::vector<PeerLink> links;  // one per overlapped communication op, in program order
+    std::vector<std::string> opened;  // IPC handles this plan holds a reference on (process-wide cache)
+    uint32_t epoch = 0;
+};
+
 struct Plan {
     cosma::Schedule schedule;
     char dtype = 'd';
@@ -47,12 +65,16 @@ struct Plan {
     // the strategy lowers (ring mates must agree on the protocol); then the ring communicators are limited to `reserved` CTAs and
     // narrow GEMMs leave as many SMs free.
     cosma::OverlapProgram overlap;
+    bool overlap_job = false;  // every active rank of the job lowers (the same value on every rank, idle ones included)
     int reserved = 0;
     cudaStream_t comm_stream = nullptr;
     std::vector<cudaEvent_t> micro_ev;  // [2 * micro-op] start / end, + 1 entry event
     bool last_run_overlapped = false;
+    Comm* parent = nullptr;  // the communicator the plan was created on (verdicts that every rank must share)
+    PeerTransport peer;      // copy-engine transport of the overlapped ops, once the arenas are bound (cosma_b200_plan_bind_arenas)
     // library-owned device arenas for the host-pointer entry point (allocated on first use)
     char* owned[3] = {nullptr, nullptr, nullptr};
+    bool owned_bound = false;  // cosma_b200_plan_bind_arenas has been tried on them
     // column-panel pipelining of the host-pointer entry point (COSMA_B200_HOST_PANELS, multiply_exec.cu): the plan of one panel
     // (m, n / c, k, same strategy, this plan's ring communicators borrowed), two B / C arena sets, copy streams and events
     bool borrowed_comms = false;

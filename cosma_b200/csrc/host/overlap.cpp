@@ -76,8 +76,17 @@ OverlapTuning overlap_tuning_from_env(char dtype, int sms) {
     };
     t.reserved_sms = static_cast<int>(num("COSMA_B200_OVERLAP_SMS", t.reserved_sms));
     t.reserved_sms = std::max(1, std::min(t.reserved_sms, t.sms / 2));
-    t.link_gbps = std::max(1.0, num("COSMA_B200_OVERLAP_GBPS", t.link_gbps));
+    // NCCL send/recv and allgather between two NVSwitch peers move ~11 GB/s per CTA when limited to a few CTAs (measured on B200:
+    // 89 GB/s with 8, 37 GB/s with 4; profiles/r2_bench_n2_*.json)
+    t.link_gbps = std::max(1.0, num("COSMA_B200_OVERLAP_GBPS", 10.5 * t.reserved_sms));
+    // planning as if the copy-engine transport were bound (tests of the panel programs without a GPU; cosma_b200_plan_bind_arenas sets it)
+    if (const char* v = std::getenv("COSMA_B200_OVERLAP_ZERO_SM"))
+        if (v[0] == 'O' && v[1] == 'N') {
+            t.zero_sm = true;
+            t.link_gbps = std::max(1.0, num("COSMA_B200_OVERLAP_GBPS", 550.0));
+        }
     t.cover = std::max(0.0, num("COSMA_B200_OVERLAP_COVER", t.cover));
+    if (t.force && !std::getenv("COSMA_B200_OVERLAP_COVER")) t.cover = 0.0;  // tests: the smallest panels that exercise every branch
     t.col_granule = std::max(1, static_cast<int>(num("COSMA_B200_OVERLAP_GRANULE", t.col_granule)));
     return t;
 }
@@ -152,154 +161,249 @@ OverlapProgram plan_overlap(const Schedule& sch, const OverlapTuning& t) {
     }
 
     Model model{t, m};
-    const int full = t.sms, narrow = std::max(1, t.sms - t.reserved_sms);
+    const int full = t.sms, narrow = t.zero_sm ? t.sms : std::max(1, t.sms - t.reserved_sms);
     const double t_ag = model.transfer_ms(ag_elems, t.link_gbps), t_ex = model.transfer_ms(ex_elems, t.link_gbps);
     const bool have_ag = ag[0] >= 0 || ag[1] >= 0;
-
-    std::vector<MicroOp>& P = out.ops;
-    auto add = [&](const MicroOp& o) {
-        P.push_back(o);
-        return static_cast<int>(P.size()) - 1;
-    };
-    bool aligned = true;
-    double est = 0.0;
-    auto gemm = [&](Range cols, Range ks, BetaMode beta, bool is_narrow, bool from_pieces, const std::vector<int>& wait) {
-        if (cols.empty() || ks.empty()) return -1;
-        MicroOp o;
-        o.kind = MicroKind::GEMM;
-        o.stream = 0;
-        o.wait = wait;
-        o.m = static_cast<int>(m);
-        o.n = static_cast<int>(cols.len());
-        o.k = static_cast<int>(ks.len());
-        o.beta = beta;
-        o.narrow = is_narrow;
-        o.lda = m; o.ldb = k; o.ldc = m;
-        if (from_pieces) {  // the gathers are still in flight: the own pieces where the caller (or an outer step) left them
-            o.a_off = ag[0] >= 0 ? ops[ag[0]].src_off + (ks.lo - Ko.lo) * m : g.a_off + ks.lo * m;
-            o.b_off = ag[1] >= 0 ? ops[ag[1]].src_off + (cols.lo - Bo.lo) * k + ks.lo : g.b_off + cols.lo * k + ks.lo;
-        } else {
-            o.a_off = g.a_off + ks.lo * m;
-            o.b_off = g.b_off + cols.lo * k + ks.lo;
-        }
-        o.c_off = g.c_off + cols.lo * m;
-        for (std::int64_t off : {o.a_off, o.b_off, o.c_off})
-            if ((off * t.elem_bytes) % 16 != 0) aligned = false;
-        est += model.gemm_ms(o.n, o.k, is_narrow ? narrow : full);
-        return add(o);
-    };
-
-    // ops before the overlapped tail run as they are, on the compute stream
-    int last_serial = -1;
-    for (int i = 0; i < first_async; ++i) {
-        MicroOp o;
-        o.kind = MicroKind::SERIAL;
-        o.op = i;
-        last_serial = add(o);
-    }
-    std::vector<int> all_ag;
-    for (int i = first_async; i < gi; ++i) {
-        MicroOp o;
-        o.kind = MicroKind::ALLGATHER;
-        o.stream = 1;
-        o.op = i;
-        if (last_serial >= 0) o.wait.push_back(last_serial);
-        all_ag.push_back(add(o));
-    }
-
     const Range all_k{0, k};
-    Range S1{0, 0};
+    const std::int64_t gr = std::max(1, t.col_granule);
+
+    // Where the first panel comes from: the own column block of B inside the peer's half of C (it is needed first anyway), else inside
+    // the own half. It sits at the OUTER end of its half, so that everything else stays contiguous around the boundary of the halves.
+    Range R1{0, 0};
     bool s1_in_mine = false;
-    double g1_ms = 0.0;
     if (have_ag) {
-        Range R1 = intersect(Bo, peer);
+        R1 = intersect(Bo, peer);
         if (R1.empty()) {
             R1 = intersect(Bo, mine);
             s1_in_mine = true;
         }
-        const std::int64_t w1 = model.choose_width(R1.len(), Ko.len(), narrow, t.cover * t_ag);
-        // at the outer end of the region, so that what is left of it stays one contiguous range
-        S1 = (R1.hi == n && R1.lo != 0) ? Range{R1.hi - w1, R1.hi} : Range{R1.lo, R1.lo + w1};
-        g1_ms = model.gemm_ms(S1.len(), Ko.len(), narrow);
-        gemm(S1, Ko, g.beta, true, true, {});
-        if (!s1_in_mine) {
-            gemm(S1, Kp, BetaMode::ONE, false, false, all_ag);
-            const Range rest = S1.lo == peer.lo ? Range{S1.hi, peer.hi} : Range{peer.lo, S1.lo};
-            gemm(rest, all_k, g.beta, false, false, all_ag);
-        } else {
-            gemm(peer, all_k, g.beta, false, false, all_ag);
-        }
-    } else {
-        gemm(peer, all_k, g.beta, false, false, {});
     }
-    double exposed = std::max(0.0, t_ag - g1_ms);
+    const bool r1_low = !(R1.hi == n && R1.lo != 0);  // the region starts at column 0 (or covers everything): the first panel is its prefix
 
-    int after = gi + 1;
-    if (red >= 0) {
-        const ScheduleOp& r = ops[red];
-        MicroOp ex;
-        ex.kind = MicroKind::EXCHANGE;
-        ex.stream = 1;
-        ex.wait.push_back(static_cast<int>(P.size()) - 1);  // the peer's half is complete
-        ex.ring_index = r.ring_index;
-        ex.peer = 1 - r.my_pos;
-        ex.send_off = r.src_off + peer.lo * m;
-        ex.count = ex_elems;
-        ex.recv_off = r.beta == BetaMode::ZERO ? r.dst_off : r.tmp_off;
-        ex.recv_off_zero = r.dst_off;
-        ex.beta = r.beta;
-        const int ex_idx = add(ex);
-        // this rank's half, the first part beside the exchange kernels
-        double narrow_ms = 0.0;
-        Range rest = mine;
-        if (s1_in_mine) {
-            if (!Kp.empty()) {
-                narrow_ms += model.gemm_ms(S1.len(), Kp.len(), narrow);
-                gemm(S1, Kp, BetaMode::ONE, true, false, all_ag);
+    // A layout = three widths. w1: the first panel (own pieces only, beside the allgathers). spill: columns of the own half computed
+    // together with the end of the peer's half, to fill that launch's last wave. wm: the panel of the own half computed beside the
+    // exchange; whatever is computed before the exchange has arrived goes to the partial buffer and is added afterwards ("early"
+    // columns), the rest is computed onto the received half directly (beta = 1).
+    struct Layout {
+        std::int64_t w1 = 0, spill = 0, wm = 0;
+    };
+    std::vector<MicroOp>& P = out.ops;
+    bool aligned = true;
+
+    // emits the program of a layout (dry: only its estimated duration, penalties for exposed transfers included)
+    auto build = [&](const Layout& L, bool dry) -> double {
+        double est = 0.0;
+        auto add = [&](const MicroOp& o) {
+            P.push_back(o);
+            return static_cast<int>(P.size()) - 1;
+        };
+        // c_override >= 0: the result goes there (element offset into the C arena) instead of into the GEMM's own result buffer
+        auto gemm = [&](Range cols, Range ks, BetaMode beta, bool is_narrow, bool from_pieces, const std::vector<int>& wait, std::int64_t c_override) {
+            if (cols.empty() || ks.empty()) return -1;
+            est += model.gemm_ms(cols.len(), ks.len(), is_narrow ? narrow : full);
+            if (dry) return -1;
+            MicroOp o;
+            o.kind = MicroKind::GEMM;
+            o.stream = 0;
+            o.wait = wait;
+            o.m = static_cast<int>(m);
+            o.n = static_cast<int>(cols.len());
+            o.k = static_cast<int>(ks.len());
+            o.beta = beta;
+            o.narrow = is_narrow && !t.zero_sm;
+            o.lda = m; o.ldb = k; o.ldc = m;
+            if (from_pieces) {  // the gathers are still in flight: the own pieces where the caller (or an outer step) left them
+                o.a_off = ag[0] >= 0 ? ops[ag[0]].src_off + (ks.lo - Ko.lo) * m : g.a_off + ks.lo * m;
+                o.b_off = ag[1] >= 0 ? ops[ag[1]].src_off + (cols.lo - Bo.lo) * k + ks.lo : g.b_off + cols.lo * k + ks.lo;
+            } else {
+                o.a_off = g.a_off + ks.lo * m;
+                o.b_off = g.b_off + cols.lo * k + ks.lo;
             }
-            rest = S1.lo == mine.lo ? Range{S1.hi, mine.hi} : Range{mine.lo, S1.lo};
-        }
-        const double need = t.cover * t_ex - narrow_ms;
-        if (need > 0.0 && !rest.empty()) {
-            const std::int64_t w = model.choose_width(rest.len(), k, narrow, need);
-            narrow_ms += model.gemm_ms(w, k, narrow);
-            gemm(Range{rest.lo, rest.lo + w}, all_k, g.beta, true, false, all_ag);
-            rest.lo += w;
-        }
-        gemm(rest, all_k, g.beta, false, false, all_ag);
-        exposed += std::max(0.0, t_ex - narrow_ms);
-        // own half of the sum: received half (+ beta * what C held) + own partial result
-        MicroOp acc;
-        acc.kind = MicroKind::ACCUMULATE;
-        acc.stream = 0;
-        acc.dst_off = r.dst_off;
-        acc.count = ex_elems;
-        acc.wait.push_back(ex_idx);
-        if (r.beta != BetaMode::ZERO) {
-            acc.add_off = r.tmp_off;
-            acc.beta = r.beta;
-            acc.beta_term = true;
-            add(acc);
-            acc.beta_term = false;  // the own-half term still waits for the exchange: it is the first to touch C when beta == 0
-        }
-        acc.add_off = r.src_off + mine.lo * m;
-        acc.beta = BetaMode::ONE;
-        add(acc);
-        est += (r.beta != BetaMode::ZERO ? 2.0 : 1.0) * model.transfer_ms(3 * ex_elems, 6000.0);
-        after = red + 1;
-    }
-    for (int i = after; i < static_cast<int>(ops.size()); ++i) {
-        MicroOp o;
-        o.kind = MicroKind::SERIAL;
-        o.op = i;
-        add(o);
-    }
+            o.c_off = c_override >= 0 ? c_override : g.c_off + cols.lo * m;
+            for (std::int64_t off : {o.a_off, o.b_off, o.c_off})
+                if ((off * t.elem_bytes) % 16 != 0) aligned = false;
+            return add(o);
+        };
 
-    const double serial_gbps = 3.0 * t.link_gbps;  // what the unconstrained NCCL kernels of the serial schedule reach
+        std::vector<int> all_ag;
+        if (!dry) {
+            // ops before the overlapped tail run as they are, on the compute stream
+            int last_serial = -1;
+            for (int i = 0; i < first_async; ++i) {
+                MicroOp o;
+                o.kind = MicroKind::SERIAL;
+                o.op = i;
+                last_serial = add(o);
+            }
+            for (int i = first_async; i < gi; ++i) {
+                MicroOp o;
+                o.kind = MicroKind::ALLGATHER;
+                o.stream = 1;
+                o.op = i;
+                if (last_serial >= 0) o.wait.push_back(last_serial);
+                all_ag.push_back(add(o));
+            }
+        }
+        // the spill: columns of the own half next to the boundary of the halves
+        Range spill{0, 0};
+        if (red >= 0 && L.spill > 0) spill = mine.lo == peer.hi ? Range{mine.lo, mine.lo + L.spill} : Range{mine.hi - L.spill, mine.hi};
+        Range S1{0, 0};
+        if (have_ag) {
+            S1 = r1_low ? Range{R1.lo, R1.lo + L.w1} : Range{R1.hi - L.w1, R1.hi};
+            const double g1 = model.gemm_ms(S1.len(), Ko.len(), narrow);
+            est += std::max(0.0, t.cover * t_ag - g1);  // what the first panel does not hide
+            gemm(S1, Ko, g.beta, true, true, {}, -1);
+            if (!s1_in_mine) {
+                gemm(S1, Kp, BetaMode::ONE, false, false, all_ag, -1);
+                // the rest of the peer's half (without a reduce: of everything) and the spill: one range next to the boundary, plus --
+                // when there is no reduce and the own block of B is the upper half -- the other half below it
+                Range rest = S1.lo == peer.lo ? Range{S1.hi, peer.hi} : Range{peer.lo, S1.lo};
+                if (!spill.empty()) rest = spill.lo == rest.hi ? Range{rest.lo, spill.hi} : Range{spill.lo, rest.hi};
+                gemm(rest, all_k, g.beta, false, false, all_ag, -1);
+            } else {
+                Range pp = peer;
+                if (!spill.empty()) pp = spill.lo == pp.hi ? Range{pp.lo, spill.hi} : Range{spill.lo, pp.hi};
+                gemm(pp, all_k, g.beta, false, false, all_ag, -1);
+            }
+        } else {
+            Range pp = peer;
+            if (!spill.empty()) pp = spill.lo == pp.hi ? Range{pp.lo, spill.hi} : Range{spill.lo, pp.hi};
+            gemm(pp, all_k, g.beta, false, false, {}, -1);
+        }
+
+        if (red >= 0) {
+            const ScheduleOp& r = ops[red];
+            int ex_idx = -1;
+            if (!dry) {
+                MicroOp ex;
+                ex.kind = MicroKind::EXCHANGE;
+                ex.stream = 1;
+                ex.wait.push_back(static_cast<int>(P.size()) - 1);  // the peer's half is complete
+                ex.ring_index = r.ring_index;
+                ex.peer = 1 - r.my_pos;
+                ex.send_off = r.src_off + peer.lo * m;
+                ex.count = ex_elems;
+                ex.recv_off = r.beta == BetaMode::ZERO ? r.dst_off : r.tmp_off;
+                ex.recv_off_zero = r.dst_off;
+                ex.beta = r.beta;
+                ex_idx = add(ex);
+            }
+            // this rank's half: [spill | ... | S1 (if it lies in this half)], the spill at the boundary, S1 at the outer end
+            std::vector<Range> early;
+            if (!spill.empty()) early.push_back(spill);
+            double beside = 0.0;  // GEMM time beside the exchange
+            Range rest = mine;
+            if (!spill.empty()) rest = spill.lo == mine.lo ? Range{spill.hi, mine.hi} : Range{mine.lo, spill.lo};
+            if (s1_in_mine) {
+                rest = S1.lo == mine.lo ? Range{S1.hi, rest.hi} : Range{rest.lo, S1.lo};
+                if (!Kp.empty()) {
+                    beside += model.gemm_ms(S1.len(), Kp.len(), narrow);
+                    gemm(S1, Kp, BetaMode::ONE, true, false, all_ag, -1);
+                }
+            }
+            if (L.wm > 0 && !rest.empty()) {
+                // next to the spill (or the boundary), so that the early columns there form one range
+                const std::int64_t w = std::min(L.wm, rest.len());
+                const bool at_low = mine.lo == peer.hi;  // the boundary is the low end of this half
+                const Range M1 = at_low ? Range{rest.lo, rest.lo + w} : Range{rest.hi - w, rest.hi};
+                beside += model.gemm_ms(M1.len(), k, narrow);
+                gemm(M1, all_k, g.beta, true, false, all_ag, -1);
+                if (!early.empty() && early.back().hi == M1.lo) early.back().hi = M1.hi;
+                else if (!early.empty() && M1.hi == early.back().lo) early.back().lo = M1.lo;
+                else early.push_back(M1);
+                rest = at_low ? Range{M1.hi, rest.hi} : Range{rest.lo, M1.lo};
+            }
+            if (s1_in_mine) early.push_back(S1);
+            est += std::max(0.0, t.cover * t_ex - beside);  // what the panels beside the exchange do not hide
+            // the received half: C = beta * C + received (skipped at run time when beta == 0: the exchange then lands in C itself)
+            MicroOp acc;
+            acc.kind = MicroKind::ACCUMULATE;
+            acc.stream = 0;
+            acc.wait.push_back(ex_idx);
+            if (r.beta != BetaMode::ZERO) {
+                acc.dst_off = r.dst_off;
+                acc.add_off = r.tmp_off;
+                acc.count = ex_elems;
+                acc.beta = r.beta;
+                acc.beta_term = true;
+                if (!dry) add(acc);
+                est += model.transfer_ms(3 * ex_elems, 6000.0);
+            }
+            // ... += the early columns of the own partial result
+            acc.beta = BetaMode::ONE;
+            acc.beta_term = false;
+            for (const Range& e : early) {
+                acc.dst_off = r.dst_off + (e.lo - mine.lo) * m;
+                acc.add_off = r.src_off + e.lo * m;
+                acc.count = e.len() * m;
+                if (!dry) add(acc);
+                est += model.transfer_ms(3 * acc.count, 6000.0) + 0.005;
+            }
+            // ... and the remaining columns computed onto it
+            if (!rest.empty()) {
+                const int gi2 = gemm(rest, all_k, BetaMode::ONE, false, false, all_ag, r.dst_off + (rest.lo - mine.lo) * m);
+                if (gi2 >= 0) P[gi2].wait.push_back(ex_idx);
+            }
+        }
+        if (!dry)
+            for (int i = (red >= 0 ? red + 1 : gi + 1); i < static_cast<int>(ops.size()); ++i) {
+                MicroOp o;
+                o.kind = MicroKind::SERIAL;
+                o.op = i;
+                add(o);
+            }
+        return est;
+    };
+
+    // choose the layout: whole waves everywhere, transfers hidden (the estimate carries a penalty for what is not)
+    Layout best;
+    {
+        const std::int64_t n1 = have_ag ? std::max<std::int64_t>(R1.len() / gr, 1) : 0;
+        const std::int64_t mine_free = red >= 0 ? mine.len() : 0;
+        if (t.force && gr < 128) {
+            // tests: small fixed panels that exercise every branch
+            best.w1 = have_ag ? std::min<std::int64_t>(gr, R1.len()) : 0;
+            const std::int64_t left = mine_free - (s1_in_mine ? best.w1 : 0);
+            best.spill = std::min<std::int64_t>(gr, std::max<std::int64_t>(left - gr, 0));
+            best.wm = std::min<std::int64_t>(gr, std::max<std::int64_t>(left - best.spill, 0));
+        } else {
+            // the round granule: the fewest column tiles that make whole waves of the full grid
+            std::int64_t c0 = 1;
+            while (c0 < 64 && (model.tiles_m() * c0) % full != 0) ++c0;
+            const std::int64_t max_spill = std::min<std::int64_t>(c0 + 1, 64);
+            double best_cost = -1.0;
+            for (std::int64_t c1 = have_ag ? 1 : 0; c1 <= n1; ++c1) {
+                Layout L;
+                L.w1 = have_ag ? (c1 == n1 ? R1.len() : c1 * gr) : 0;
+                const std::int64_t left = mine_free - (s1_in_mine ? L.w1 : 0);
+                for (std::int64_t e = 0; e <= max_spill && e * gr <= left; ++e) {
+                    L.spill = e * gr;
+                    L.wm = 0;
+                    const double c = build(L, true);
+                    if (best_cost < 0.0 || c < best_cost - 1e-9) { best_cost = c; best = L; }
+                    if (red < 0) break;
+                }
+                if (!have_ag) break;
+            }
+            if (red >= 0) {
+                const std::int64_t left = mine_free - (s1_in_mine ? best.w1 : 0) - best.spill;
+                Layout L = best;
+                for (std::int64_t c = 0; c * gr <= left; ++c) {
+                    L.wm = c * gr;
+                    const double cst = build(L, true);
+                    if (cst < best_cost - 1e-9) { best_cost = cst; best = L; }
+                }
+            }
+        }
+    }
+    P.clear();
+    aligned = true;
+    const double est = build(best, false);
+
     out.est_comm_ms = t_ag + t_ex;
-    out.est_serial_ms = model.gemm_ms(n, k, full) + model.transfer_ms(ag_elems + ex_elems, serial_gbps) +
+    out.est_serial_ms = model.gemm_ms(n, k, full) + model.transfer_ms(ag_elems + ex_elems, t.serial_gbps) +
                         (red >= 0 && ops[red].beta != BetaMode::ZERO ? model.transfer_ms(3 * ex_elems, 6000.0) : 0.0);
-    out.est_overlap_ms = est + exposed;
+    out.est_overlap_ms = est;
     if (!t.force) {
         if (!aligned) return no("a panel would not start on a 16-byte boundary");
         if (out.est_overlap_ms >= out.est_serial_ms) return no("estimated no gain over the serial schedule");

@@ -292,6 +292,9 @@ int get_state(Comm* c, char dtype, int m, int n, int k, const char* steps, const
             }
         }
     }
+    // the arenas never change: overlapped transfers of the multiply go through copy engines (collective; no-op for other plans)
+    rc = cosma_b200_plan_bind_arenas(st->plan, st->arena[0], st->arena[1], st->arena[2], nullptr);
+    if (rc != COSMA_B200_OK) return rc;
     *out = st.get();
     c->layout_states[key] = st.release();
     return COSMA_B200_OK;

@@ -10,6 +10,7 @@
 #include "gemm_tf32x3_sm100.h"
 #include "host_stream.h"
 #include "cta_budget.h"
+#include "peer_transport.h"
 
 #include <cstring>
 
@@ -168,6 +169,21 @@ int plan_run_overlapped(Plan& plan, const double* alpha, const double* beta, cha
     // the communication stream starts after whatever the caller queued (the operands are where they should be)
     CUDA_TRY(cudaEventRecord(entry, stream));
     CUDA_TRY(cudaStreamWaitEvent(comm, entry, 0));
+    // zero-SM transport (peer_transport.h): copy-engine pushes into the ring mates' arenas instead of NCCL kernels
+    PeerTransport& peer = plan.peer;
+    const bool ce = peer.ready;
+    if (ce) {
+        if (arenas[0] != peer.bound[0] || arenas[1] != peer.bound[1] || arenas[2] != peer.bound[2]) {
+            set_last_error("multiply: the arenas differ from the ones bound to the plan (cosma_b200_plan_bind_arenas): bind the new ones first");
+            return COSMA_B200_INVALID_ARG;
+        }
+        ++peer.epoch;
+        for (const auto& link : peer.links) {  // every mate learns that this rank's previous call has drained
+            const int st = peer_signal_entered(peer, link, comm);
+            if (st != COSMA_B200_OK) return st;
+        }
+    }
+    std::vector<int> pending;  // allgathers whose pushes are queued but whose arrival has not been waited for yet
     int last_comm = -1;
     for (size_t i = 0; i < prog.size(); ++i) {
         const cosma::MicroOp& o = prog[i];
@@ -176,6 +192,41 @@ int plan_run_overlapped(Plan& plan, const double* alpha, const double* beta, cha
             if (prog[w].stream != o.stream) CUDA_TRY(cudaStreamWaitEvent(s, plan.micro_ev[2 * w + 1], 0));
         if (plan.time_gemms) CUDA_TRY(cudaEventRecord(plan.micro_ev[2 * i], s));
         int st = COSMA_B200_OK;
+        bool record_end = true;
+        if (ce && o.stream == 1 && (o.kind == cosma::MicroKind::ALLGATHER || o.kind == cosma::MicroKind::EXCHANGE)) {
+            const PeerLink* link = peer_link(peer, static_cast<int>(i));
+            if (!link) return COSMA_B200_INTERNAL_ERROR;
+            if (o.kind == cosma::MicroKind::ALLGATHER) {
+                // own piece: to the mate (copy engine over NVLink) and into the own slot of the expanded buffer; every push is queued
+                // before the first wait for an arrival, so the transfers of consecutive allgathers are all in flight together
+                const auto& op = ops[o.op];
+                const int64_t cnt = op.piece[0][0];
+                const char* src = arenas[op.matrix] + op.src_off * EB;
+                st = peer_push(peer, *link, src, static_cast<size_t>(cnt * EB), false, s);
+                if (st != COSMA_B200_OK) return st;
+                CUDA_TRY(cudaMemcpyAsync(arenas[op.matrix] + (op.dst_off + op.my_pos * cnt) * EB, src, static_cast<size_t>(cnt * EB), cudaMemcpyDeviceToDevice, s));
+                pending.push_back(static_cast<int>(i));
+                const bool more = i + 1 < prog.size() && prog[i + 1].stream == 1 && prog[i + 1].kind == cosma::MicroKind::ALLGATHER;
+                if (!more) {
+                    for (int j : pending) {
+                        st = peer_wait_arrived(peer, *peer_link(peer, j), s);
+                        if (st != COSMA_B200_OK) return st;
+                        CUDA_TRY(cudaEventRecord(plan.micro_ev[2 * j + 1], s));
+                    }
+                    pending.clear();
+                }
+                record_end = false;
+            } else {
+                double b[2];
+                beta_of(o.beta, beta, E, b);
+                st = peer_push(peer, *link, arenas[2] + o.send_off * EB, static_cast<size_t>(o.count * EB), b[0] == 0.0 && b[1] == 0.0, s);
+                if (st == COSMA_B200_OK) st = peer_wait_arrived(peer, *link, s);
+                if (st != COSMA_B200_OK) return st;
+            }
+            if (record_end) CUDA_TRY(cudaEventRecord(plan.micro_ev[2 * i + 1], s));
+            last_comm = static_cast<int>(i);
+            continue;
+        }
         switch (o.kind) {
             case cosma::MicroKind::GEMM: {
                 double b[2];
@@ -595,7 +646,9 @@ static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int 
                 plan->overlap.why = !why.empty() ? why : (!tuning.enabled ? "switched off (COSMA_OVERLAP_COMM_AND_COMP)" : "not a multi-rank schedule of at most 64 ranks");
             }
             use_ring_config = all;
+            plan->overlap_job = all;
         }
+        plan->parent = c;
         if (c && nranks > 1) {
             const auto* N = nccl();
             // overlapped plans: the ring communicators' kernels are limited to the SMs the narrow GEMMs leave free
@@ -639,6 +692,7 @@ int cosma_b200_plan_destroy(void* plan) {
         for (auto c : p->ring_comms)
             if (c && nccl()) nccl()->CommDestroy(c);
     for (auto e : p->ev) cudaEventDestroy(e);
+    cosma_b200::peer_transport_release(p->peer);
     for (auto e : p->micro_ev) cudaEventDestroy(e);
     if (p->comm_stream) cudaStreamDestroy(p->comm_stream);
     for (auto& a : p->owned)
@@ -753,7 +807,14 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
     return guarded("cosma_b200_multiply_host", [&]() -> int {
         Plan* p = static_cast<Plan*>(plan);
         if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
-        if (p->schedule.idle()) return COSMA_B200_OK;
+        if (p->schedule.idle()) {
+            // idle ranks take part in the one collective of this entry point: the verdict of the arena binding (first call)
+            if (p->overlap_job && !p->owned_bound) {
+                p->owned_bound = true;
+                return cosma_b200_plan_bind_arenas(p, nullptr, nullptr, nullptr, nullptr);
+            }
+            return COSMA_B200_OK;
+        }
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if (const int panels = cosma_b200::host_panels_requested()) {
             bool handled = false;
@@ -769,6 +830,11 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
                     return COSMA_B200_OUT_OF_MEMORY;
                 }
             }
+        if (p->overlap_job && !p->owned_bound) {  // the plan's own arenas: copy-engine transport for the overlapped transfers (collective)
+            p->owned_bound = true;
+            const int rc = cosma_b200_plan_bind_arenas(p, p->owned[0], p->owned[1], p->owned[2], nullptr);
+            if (rc != COSMA_B200_OK) return rc;
+        }
         const bool beta_zero = beta[0] == 0.0 && (p->elem_reals == 1 || beta[1] == 0.0);
         // A schedule with ONE base-case GEMM that reads a local matrix as the caller holds it (no allgather of that matrix
         // before it) / leaves local C as the caller wants it (no reduce after it) streams that matrix over PCIe under the
@@ -811,6 +877,51 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
         if (rc != COSMA_B200_OK) return rc;
         const size_t cbytes = p->schedule.initial_elements(2) * es;
         if (!streamed[2] && cbytes && cudaMemcpyAsync(C, p->owned[2], cbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return COSMA_B200_CUDA_ERROR;
+        return COSMA_B200_OK;
+    });
+}
+
+/* Binds the device arenas the plan will be run on (collective over the plan's communicator: every rank calls it, idle ranks too). An
+ * overlapped plan (cosma_b200_plan_overlap_export) then moves its ring-of-two transfers with COPY ENGINES straight into the ring
+ * mates' arenas (CUDA IPC) instead of NCCL kernels, and re-plans its panels for a device that no longer shares SMs with communication.
+ * *active = 1 when that transport is in place (on every rank alike); 0: nothing changes (plan not overlapped, COSMA_B200_PEER_COPY=OFF,
+ * or some rank could not map its mate's memory). cosma_b200_multiply must then be called with exactly these arenas. */
+int cosma_b200_plan_bind_arenas(void* plan, void* A, void* B, void* C, int* active) {
+    return guarded("cosma_b200_plan_bind_arenas", [&]() -> int {
+        Plan* p = static_cast<Plan*>(plan);
+        if (active) *active = 0;
+        if (!p) return COSMA_B200_INVALID_ARG;
+        if (!p->overlap_job || !p->parent || !cosma_b200::peer_copy_enabled()) return COSMA_B200_OK;
+        if (!p->schedule.idle() && (!A || !B || !C)) return COSMA_B200_INVALID_ARG;
+        COSMA_B200_CUDA_TRY(cudaDeviceSynchronize());  // an earlier multiply on the previous transport may still be running
+        bool ok = false;
+        const int st = cosma_b200::peer_transport_setup(*p, p->parent, A, B, C, &ok);
+        if (st != COSMA_B200_OK) return st;
+        if (ok && p->overlap.enabled) {
+            // the same lowering for a transport that costs no SM: every panel on the whole device, transfers at the NVLink copy rate
+            int sms = 0, dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+            cosma::OverlapTuning tuning = cosma::overlap_tuning_from_env(p->dtype, sms);
+            tuning.zero_sm = true;
+            tuning.force = true;  // the verdict "every rank lowers" has been taken at plan creation
+            if (!std::getenv("COSMA_B200_OVERLAP_GBPS")) tuning.link_gbps = 550.0;  // peer copy over NVLink 5 (measured on this pool: ~770 one way)
+            cosma::OverlapProgram prog = cosma::plan_overlap(p->schedule, tuning);
+            if (!prog.enabled) {
+                set_last_error("bind_arenas: the overlapped program could not be rebuilt: " + prog.why);
+                return COSMA_B200_INTERNAL_ERROR;
+            }
+            // the transport's links name micro-ops by index: the communication ops keep their order, so re-index them
+            std::vector<int> comm_ops;
+            for (size_t i = 0; i < prog.ops.size(); ++i)
+                if (prog.ops[i].stream == 1 && (prog.ops[i].kind == cosma::MicroKind::ALLGATHER || prog.ops[i].kind == cosma::MicroKind::EXCHANGE)) comm_ops.push_back(static_cast<int>(i));
+            if (comm_ops.size() != p->peer.links.size()) return COSMA_B200_INTERNAL_ERROR;
+            for (size_t l = 0; l < comm_ops.size(); ++l) p->peer.links[l].micro = comm_ops[l];
+            prog.why += " (copy-engine peer transport)";
+            p->overlap = std::move(prog);
+            for (auto e : p->micro_ev) cudaEventDestroy(e);
+            p->micro_ev.clear();
+        }
+        if (active) *active = ok ? 1 : 0;
         return COSMA_B200_OK;
     });
 }

@@ -36,6 +36,7 @@ def _declare(lib):
     lib.cosma_b200_plan_last_launches.argtypes = [vp]
     lib.cosma_b200_plan_time_gemms.argtypes = [vp, ci]
     lib.cosma_b200_plan_gemm_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci, ctypes.POINTER(ci)]
+    lib.cosma_b200_plan_bind_arenas.argtypes = [vp, vp, vp, vp, ctypes.POINTER(ci)]
     lib.cosma_b200_plan_overlap_export.argtypes = [vp, ctypes.POINTER(i64), i64, ctypes.POINTER(i64), ctypes.POINTER(ci), ctypes.c_char_p, ci,
                                                    ctypes.POINTER(ctypes.c_double)]
     lib._dist_declared = True
@@ -159,6 +160,14 @@ class MultiplyPlan:
                 arena = torch.zeros(max(self.arena_elements[x], 1), dtype=tdt, device=dev)
                 mats.append(LocalMatrix(label, arena, self.initial_elements[x]))
             self.A, self.B, self.C = mats
+            # the arenas are fixed for the plan's life: overlapped transfers can go through copy engines into the ring mates' arenas
+            # (collective over the communicator; nothing changes for plans that are not overlapped)
+            self.peer_copy = False
+            if comm is not None and self.nranks > 1:
+                act = ctypes.c_int(0)
+                _lib.check(lib.cosma_b200_plan_bind_arenas(h, ctypes.c_void_p(self.A.arena.data_ptr()), ctypes.c_void_p(self.B.arena.data_ptr()),
+                                                           ctypes.c_void_p(self.C.arena.data_ptr()), ctypes.byref(act)), "cosma_b200_plan_bind_arenas")
+                self.peer_copy = bool(act.value)
 
     def ops(self):
         n = ctypes.c_int64(0)

@@ -54,8 +54,10 @@ struct OverlapTuning {
     bool force = false;         // lower whenever the shape of the op list allows it, whatever the estimated gain (tests)
     int sms = 148;              // SMs of the device (the same on every rank)
     int reserved_sms = 8;       // SMs (= NCCL CTAs) left to the communication kernels during narrow GEMMs
-    double link_gbps = 150.0;   // assumed NCCL point-to-point rate with `reserved_sms` CTAs
-    double cover = 1.5;         // a narrow GEMM lasts >= cover x the estimated transfer it hides
+    double link_gbps = 84.0;    // NCCL point-to-point rate with `reserved_sms` CTAs (measured: ~10.5 GB/s per CTA)
+    double cover = 1.25;        // a narrow GEMM lasts >= cover x the estimated transfer it hides
+    bool zero_sm = false;       // the transfers use no SM (copy engines, csrc/peer_transport.h): no narrow launches
+    double serial_gbps = 450.0; // what the unconstrained NCCL kernels of the serial schedule reach (for the gain estimate)
     int col_granule = 128;      // panel widths are multiples of this (the GEMM tile width)
     int elem_bytes = 8;
     bool complex_type = false;

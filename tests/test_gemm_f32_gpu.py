@@ -5,6 +5,10 @@ formed in FP64 from the same FP32 inputs (stricter than comparing with an FP32 B
 Integer-valued inputs (Tiled-MM convention, libs/Tiled-MM/tests/test-multiply.cpp:60-68) are exact in TF32, so those
 cases must be BIT-exact against the oracle's naive loop (reference src/cosma/local_multiply.cpp:277-297). The
 reference's own element-wise criterion for float (utils/cosma_utils.hpp:366-377, 1e-5) is checked too."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -12,6 +16,8 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-6
+# COSMA_B200_TF32_KERNEL = v1 | v2 (csrc/gemm_tf32x3_sm100.cu): v1 has no tensor path for CGEMM with a transposed / conjugated operand
+V1_ONLY = os.environ.get("COSMA_B200_TF32_KERNEL", "").lower().startswith("v1")
 
 
 def _run(oracle, dtype, ta, tb, m, n, k, alpha, beta, pad=0, ints=False, seed=0, expect_path=None):
@@ -24,7 +30,7 @@ def _run(oracle, dtype, ta, tb, m, n, k, alpha, beta, pad=0, ints=False, seed=0,
     lda, ldb, ldc = max(1, ar + pad), max(1, br + pad), max(1, m + pad)
     if expect_path is None:  # TMA needs 16-byte row pitches: ld % 4 == 0 (float), ld % 2 == 0 (complex float)
         q = 2 if cplx else 4
-        expect_path = 1 if (lda % q == 0 and ldb % q == 0 and (not cplx or (ta == "N" and tb == "N"))) else 2
+        expect_path = 1 if (lda % q == 0 and ldb % q == 0 and (not cplx or not V1_ONLY or (ta == "N" and tb == "N"))) else 2
 
     def fill(cols, ld):
         cnt = max(1, ld * cols)
@@ -94,11 +100,20 @@ def test_cgemm_nn(oracle, m, n, k):
     _run(oracle, "c", "N", "N", m, n, k, 0.5 + 1j, 2.0 - 1j, seed=2)
 
 
+@pytest.mark.parametrize("ta,tb", [("N", "T"), ("N", "C"), ("T", "N"), ("C", "N"), ("T", "T"), ("C", "C"), ("T", "C"), ("C", "T")])
+def test_cgemm_transposes(oracle, ta, tb):
+    """op(A), op(B) in {T, C}: the split stages of the second-generation kernel build the real embedding of op(A) and the real view of
+    op(B) from either storage order (conjugation = a sign flip); the first generation sends these to the generic kernel."""
+    for (m, n, k) in ((128, 128, 64), (300, 260, 200), (65, 63, 17)):
+        _run(oracle, "c", ta, tb, m, n, k, 1.0, 0.0, ints=True)
+        _run(oracle, "c", ta, tb, m, n, k, 0.5 - 1j, 1.0 + 0.5j, seed=3)
+
+
 def test_generic_paths(oracle):
-    # unaligned leading dimensions -> generic kernel; CGEMM with conjugate-transposed A -> generic kernel
+    # unaligned leading dimensions -> generic kernel
     _run(oracle, "s", "N", "N", 100, 90, 80, 1.0, 1.0, pad=1, expect_path=2)
-    _run(oracle, "c", "C", "N", 64, 64, 64, 1.0, 0.0, expect_path=2)
-    _run(oracle, "c", "N", "T", 60, 50, 40, 2.0, 1.0, expect_path=2)
+    _run(oracle, "c", "C", "N", 64, 64, 64, 1.0, 0.0, pad=1, expect_path=2)
+    _run(oracle, "c", "N", "T", 60, 50, 40, 2.0, 1.0, pad=1, expect_path=2)
 
 
 def test_padded_ld_and_degenerate(oracle):
@@ -107,3 +122,13 @@ def test_padded_ld_and_degenerate(oracle):
     _run(oracle, "s", "N", "N", 100, 100, 0, 1.0, 2.0, ints=True)     # k = 0: C *= beta
     _run(oracle, "s", "N", "N", 0, 10, 10, 1.0, 0.0)
     _run(oracle, "s", "N", "N", 64, 64, 64, 0.0, 0.0, ints=True)      # alpha = 0, beta = 0: zeros, NaN not propagated
+
+
+@pytest.mark.skipif("COSMA_B200_TF32_KERNEL" in os.environ, reason="already a run with an explicit kernel generation")
+@pytest.mark.parametrize("generation", ["v1", "v2"])
+def test_both_kernel_generations(generation):
+    """The whole module again with the kernel generation forced (whichever is the default, the other one stays covered)."""
+    env = dict(os.environ, COSMA_B200_TF32_KERNEL=generation)
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"], capture_output=True, text=True,
+                         timeout=900, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
