@@ -7,6 +7,7 @@
 #include <sstream>
 #include <string>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -81,6 +82,32 @@ bool bind_to_device_numa_node(int device) {
 namespace {
 std::mutex g_mu;
 std::map<unsigned long long, void*> g_comms;
+
+void release_key(unsigned long long key) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_comms.find(key);
+    if (it == g_comms.end()) return;
+    cosma_b200_comm_destroy(it->second);
+    g_comms.erase(it);
+}
+
+#if defined(COSMA_B200_WITH_MPI)
+// MPI recycles communicator handles (and their Fortran indices, the cache key) after MPI_Comm_free / Cblacs_gridexit: a cached NCCL
+// communicator must die WITH its MPI communicator, or a later communicator that happens to get the same handle would inherit peers
+// that are not its own. An attribute with a delete callback does that -- also for applications that only ever call p?gemm_ and can
+// never call release_comm() (the reference needs no such hook: it compares communicators with MPI_Comm_compare, context.cpp:80-125).
+int g_keyval = MPI_KEYVAL_INVALID;
+int on_comm_free(MPI_Comm, int, void* attribute_val, void*) {
+    release_key(static_cast<unsigned long long>(reinterpret_cast<std::uintptr_t>(attribute_val)));
+    return MPI_SUCCESS;
+}
+void attach_to_comm(MPI_Comm comm, unsigned long long key) {
+    if (g_keyval == MPI_KEYVAL_INVALID && MPI_Comm_create_keyval(MPI_COMM_NULL_COPY_FN, on_comm_free, &g_keyval, nullptr) != MPI_SUCCESS) return;
+    MPI_Comm_set_attr(comm, g_keyval, reinterpret_cast<void*>(static_cast<std::uintptr_t>(key)));
+}
+#else
+void attach_to_comm(MPI_Comm, unsigned long long) {}  // process-group ids are never reused
+#endif
 }  // namespace
 
 void* comm_handle(MPI_Comm comm) {
@@ -103,6 +130,7 @@ void* comm_handle(MPI_Comm comm) {
     check(cosma_b200_comm_create(rank, size, size > 1 ? id : nullptr, &handle), "cosma_b200_comm_create");
     trace("comm_handle: communicator ready");
     g_comms[key] = handle;
+    attach_to_comm(comm, key);
     return handle;
 }
 
@@ -134,13 +162,7 @@ MPI_Comm active_comm(MPI_Comm comm, int P) {
     return sub;
 }
 
-void release_comm(MPI_Comm comm) {
-    std::lock_guard<std::mutex> lock(g_mu);
-    auto it = g_comms.find(comm_key(comm));
-    if (it == g_comms.end()) return;
-    cosma_b200_comm_destroy(it->second);
-    g_comms.erase(it);
-}
+void release_comm(MPI_Comm comm) { release_key(comm_key(comm)); }
 
 void release_all_comms() {
     std::lock_guard<std::mutex> lock(g_mu);

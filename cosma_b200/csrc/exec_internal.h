@@ -71,7 +71,9 @@ struct Plan {
     std::vector<cudaEvent_t> micro_ev;  // [2 * micro-op] start / end, + 1 entry event
     bool last_run_overlapped = false;
     Comm* parent = nullptr;  // the communicator the plan was created on (verdicts that every rank must share)
-    PeerTransport peer;      // copy-engine transport of the overlapped ops, once the arenas are bound (cosma_b200_plan_bind_arenas)
+    // copy-engine transports of the overlapped ops, one per bound set of arenas (cosma_b200_plan_bind_arenas: the caller's arenas, the
+    // plan's own ones of the host-pointer entry point); a multiply on arenas that are not bound uses NCCL
+    std::vector<std::unique_ptr<PeerTransport>> peers;
     // library-owned device arenas for the host-pointer entry point (allocated on first use)
     char* owned[3] = {nullptr, nullptr, nullptr};
     bool owned_bound = false;  // cosma_b200_plan_bind_arenas has been tried on them

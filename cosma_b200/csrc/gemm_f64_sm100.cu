@@ -627,8 +627,8 @@ static int gemm_f64_impl(cudaStream_t stream, char transa, char transb, int64_t 
             return COSMA_B200_OK;
         }
     }
-    // opt-in: repack what TMA cannot address (odd leading dimension / 8-byte-aligned base) and run the DMMA kernel on the copies
-    if (!aligned && repack_unaligned_enabled() && k >= 64 && m * n >= 128 * 128) {
+    // repack what TMA cannot address (repack.h: COSMA_B200_REPACK_UNALIGNED = AUTO | ON | OFF) (odd leading dimension / 8-byte-aligned base) and run the DMMA kernel on the copies
+    if (!aligned && repack_wanted(m, n, k)) {
         const bool a_bad = (!CPLX && (lda & 1)) || (reinterpret_cast<uintptr_t>(A) & 15);
         const bool b_bad = (!CPLX && (ldb & 1)) || (reinterpret_cast<uintptr_t>(B) & 15);
         Repacked ra, rb;

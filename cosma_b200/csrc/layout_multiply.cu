@@ -182,8 +182,8 @@ const NativeGrids& native_grids(int nranks, int m, int n, int k, const char* ste
 }
 
 bool relabelling_enabled() {
-    // opt-in until the relabelled path has run on multi-GPU hardware (the reference always relabels)
-    static const bool on = cosma::get_bool_env_var("COSMA_B200_REORDER_RANKS", false);
+    // as the reference, which always relabels (multiply.cpp:136-152); COSMA_B200_REORDER_RANKS=OFF keeps the caller's labels
+    static const bool on = cosma::get_bool_env_var("COSMA_B200_REORDER_RANKS", true);
     return on;
 }
 

@@ -170,13 +170,13 @@ int plan_run_overlapped(Plan& plan, const double* alpha, const double* beta, cha
     CUDA_TRY(cudaEventRecord(entry, stream));
     CUDA_TRY(cudaStreamWaitEvent(comm, entry, 0));
     // zero-SM transport (peer_transport.h): copy-engine pushes into the ring mates' arenas instead of NCCL kernels
-    PeerTransport& peer = plan.peer;
-    const bool ce = peer.ready;
+    PeerTransport* found = nullptr;
+    for (auto& t : plan.peers)
+        if (t->ready && arenas[0] == t->bound[0] && arenas[1] == t->bound[1] && arenas[2] == t->bound[2]) found = t.get();
+    static PeerTransport none;
+    PeerTransport& peer = found ? *found : none;
+    const bool ce = found != nullptr;  // arenas that were never bound: NCCL kernels (every rank decides alike: the calls are collective)
     if (ce) {
-        if (arenas[0] != peer.bound[0] || arenas[1] != peer.bound[1] || arenas[2] != peer.bound[2]) {
-            set_last_error("multiply: the arenas differ from the ones bound to the plan (cosma_b200_plan_bind_arenas): bind the new ones first");
-            return COSMA_B200_INVALID_ARG;
-        }
         ++peer.epoch;
         for (const auto& link : peer.links) {  // every mate learns that this rank's previous call has drained
             const int st = peer_signal_entered(peer, link, comm);
@@ -692,7 +692,8 @@ int cosma_b200_plan_destroy(void* plan) {
         for (auto c : p->ring_comms)
             if (c && nccl()) nccl()->CommDestroy(c);
     for (auto e : p->ev) cudaEventDestroy(e);
-    cosma_b200::peer_transport_release(p->peer);
+    for (auto& t : p->peers) cosma_b200::peer_transport_release(*t);
+    p->peers.clear();
     for (auto e : p->micro_ev) cudaEventDestroy(e);
     if (p->comm_stream) cudaStreamDestroy(p->comm_stream);
     for (auto& a : p->owned)
@@ -895,8 +896,24 @@ int cosma_b200_plan_bind_arenas(void* plan, void* A, void* B, void* C, int* acti
         if (!p->schedule.idle() && (!A || !B || !C)) return COSMA_B200_INVALID_ARG;
         COSMA_B200_CUDA_TRY(cudaDeviceSynchronize());  // an earlier multiply on the previous transport may still be running
         bool ok = false;
-        const int st = cosma_b200::peer_transport_setup(*p, p->parent, A, B, C, &ok);
+        // one transport per set of arenas; a set bound again is set up afresh, at most four sets are kept (oldest dropped first; the
+        // same on every rank)
+        std::unique_ptr<cosma_b200::PeerTransport> fresh(new cosma_b200::PeerTransport);
+        for (size_t i = 0; i < p->peers.size(); ++i)
+            if (p->peers[i]->bound[0] == A && p->peers[i]->bound[1] == B && p->peers[i]->bound[2] == C) {
+                cosma_b200::peer_transport_release(*p->peers[i]);
+                p->peers.erase(p->peers.begin() + i);
+                break;
+            }
+        if (p->peers.size() >= 4) {
+            cosma_b200::peer_transport_release(*p->peers.front());
+            p->peers.erase(p->peers.begin());
+        }
+        const int st = cosma_b200::peer_transport_setup(*p, *fresh, p->parent, A, B, C, &ok);
         if (st != COSMA_B200_OK) return st;
+        fresh->bound[0] = A; fresh->bound[1] = B; fresh->bound[2] = C;  // remembered also when the set-up was refused
+        p->peers.push_back(std::move(fresh));
+        cosma_b200::PeerTransport& bound_now = *p->peers.back();
         if (ok && p->overlap.enabled) {
             // the same lowering for a transport that costs no SM: every panel on the whole device, transfers at the NVLink copy rate
             int sms = 0, dev = 0;
@@ -914,8 +931,13 @@ int cosma_b200_plan_bind_arenas(void* plan, void* A, void* B, void* C, int* acti
             std::vector<int> comm_ops;
             for (size_t i = 0; i < prog.ops.size(); ++i)
                 if (prog.ops[i].stream == 1 && (prog.ops[i].kind == cosma::MicroKind::ALLGATHER || prog.ops[i].kind == cosma::MicroKind::EXCHANGE)) comm_ops.push_back(static_cast<int>(i));
-            if (comm_ops.size() != p->peer.links.size()) return COSMA_B200_INTERNAL_ERROR;
-            for (size_t l = 0; l < comm_ops.size(); ++l) p->peer.links[l].micro = comm_ops[l];
+            // (every transport of the plan: the earlier ones were indexed against the program they were set up with)
+            for (auto& t : p->peers) {
+                if (!t->ready) continue;
+                if (comm_ops.size() != t->links.size()) return COSMA_B200_INTERNAL_ERROR;
+                for (size_t l = 0; l < comm_ops.size(); ++l) t->links[l].micro = comm_ops[l];
+            }
+            (void)bound_now;
             prog.why += " (copy-engine peer transport)";
             p->overlap = std::move(prog);
             for (auto e : p->micro_ev) cudaEventDestroy(e);

@@ -147,11 +147,10 @@ const PeerLink* peer_link(const PeerTransport& t, int micro) {
     return nullptr;
 }
 
-int peer_transport_setup(Plan& plan, Comm* parent, void* A, void* B, void* C, bool* ok) {
+int peer_transport_setup(Plan& plan, PeerTransport& t, Comm* parent, void* A, void* B, void* C, bool* ok) {
     *ok = false;
     const NcclApi* N = nccl();
     if (!N || !parent || !parent->comm) return COSMA_B200_OK;
-    PeerTransport& t = plan.peer;
     peer_transport_release(t);
     char* arenas[3] = {static_cast<char*>(A), static_cast<char*>(B), static_cast<char*>(C)};
     const int64_t EB = plan.elem_bytes();

@@ -17,7 +17,7 @@ namespace cosma_b200 {
 bool peer_copy_enabled();  // COSMA_B200_PEER_COPY = ON (default) | OFF
 // Collective over the plan's ring communicators (and, for the verdict, over `parent`): exchanges landing zones and flags with every ring
 // mate. *ok = false (on every rank alike) when some rank could not set it up; the plan then keeps the NCCL transport.
-int peer_transport_setup(Plan& plan, Comm* parent, void* A, void* B, void* C, bool* ok);
+int peer_transport_setup(Plan& plan, PeerTransport& t, Comm* parent, void* A, void* B, void* C, bool* ok);
 void peer_transport_release(PeerTransport& t);
 const PeerLink* peer_link(const PeerTransport& t, int micro);
 

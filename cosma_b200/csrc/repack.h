@@ -1,7 +1,10 @@
 // Operands the TMA path cannot address (base not 16-byte aligned, or a row pitch that is not a multiple of 16 bytes -- COSMA's native
 // layout has ld = local rows, so irregular splits produce odd ones) are copied ONCE into a stream-ordered scratch with a legal
-// pitch; the tensor-pipe kernel then runs on the copy. One HBM-bound 2-D device copy per operand against an O(mnk) GEMM.
-// Opt-in (COSMA_B200_REPACK_UNALIGNED=ON) until measured on a GPU; off: the generic kernel, as before.
+// pitch by a coalesced copy kernel (repack.cu, HBM-bound); the tensor-pipe kernel then runs on the copy.
+// COSMA_B200_REPACK_UNALIGNED = AUTO (default) | ON | OFF. Measured on B200 (profiles/r2_repack_probe.jsonl, 8191 x 8192 x 8191 FP64): the
+// generic kernel reaches 12.8 TFLOP/s against 36 for the tensor-pipe kernel, so two extra passes over A and B (16 (mk + kn) bytes at
+// ~4 TB/s) pay as soon as the product is more than a few hundred cubed: AUTO repacks when m n k >= 2^27 and k >= 64; ON whenever the
+// kernel's tiles are not mostly padding (k >= 64, m n >= 128^2); OFF: the generic kernel, as in round 1.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -11,12 +14,12 @@
 
 namespace cosma_b200 {
 
-inline bool repack_unaligned_enabled() {
-    static const bool on = [] {
-        const char* v = std::getenv("COSMA_B200_REPACK_UNALIGNED");
-        return v && (!std::strcmp(v, "ON") || !std::strcmp(v, "on") || !std::strcmp(v, "1") || !std::strcmp(v, "TRUE") || !std::strcmp(v, "true"));
-    }();
-    return on;
+int repack_mode();  // 0 off, 1 on, 2 auto
+
+inline bool repack_wanted(int64_t m, int64_t n, int64_t k) {
+    const int mode = repack_mode();
+    if (mode == 0 || k < 64 || m * n < 128 * 128) return false;
+    return mode == 1 || static_cast<double>(m) * static_cast<double>(n) * static_cast<double>(k) >= 134217728.0;
 }
 
 struct Repacked {
@@ -26,23 +29,8 @@ struct Repacked {
 
 // Copies the stored rows x cols operand (column-major, leading dimension ld, elements of elem_bytes) into a scratch whose leading
 // dimension is rows rounded up to a multiple of ld_multiple elements. Returns cudaSuccess and out.ptr != nullptr on success.
-inline cudaError_t repack_operand(cudaStream_t stream, const void* src, int64_t ld, int64_t rows, int64_t cols, int elem_bytes, int ld_multiple,
-                                  Repacked& out) {
-    out.ld = (rows + ld_multiple - 1) / ld_multiple * ld_multiple;
-    if (out.ld < 1) out.ld = ld_multiple;
-    const size_t bytes = static_cast<size_t>(out.ld) * static_cast<size_t>(cols > 0 ? cols : 1) * elem_bytes;
-    cudaError_t e = cudaMallocAsync(&out.ptr, bytes, stream);
-    if (e != cudaSuccess) { out.ptr = nullptr; return e; }
-    if (rows > 0 && cols > 0)
-        e = cudaMemcpy2DAsync(out.ptr, static_cast<size_t>(out.ld) * elem_bytes, src, static_cast<size_t>(ld) * elem_bytes,
-                              static_cast<size_t>(rows) * elem_bytes, static_cast<size_t>(cols), cudaMemcpyDeviceToDevice, stream);
-    if (e != cudaSuccess) { cudaFreeAsync(out.ptr, stream); out.ptr = nullptr; }
-    return e;
-}
-
-inline void repack_release(cudaStream_t stream, Repacked& r) {
-    if (r.ptr) cudaFreeAsync(r.ptr, stream);
-    r.ptr = nullptr;
-}
+cudaError_t repack_operand(cudaStream_t stream, const void* src, int64_t ld, int64_t rows, int64_t cols, int elem_bytes, int ld_multiple,
+                           Repacked& out);
+void repack_release(cudaStream_t stream, Repacked& r);
 
 }  // namespace cosma_b200

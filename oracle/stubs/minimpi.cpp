@@ -504,7 +504,28 @@ int MPI_Comm_dup(MPI_Comm c, MPI_Comm* n) {
     *n = make_comm(p.world, fresh_ctx(p.world, p.ctx, TAG_COLL - 1));
     return 0;
 }
+// communicator attributes: delete callbacks run when the communicator is freed
+static std::vector<std::pair<MPI_Comm_delete_attr_function*, void*>> g_keyvals;
+static std::map<std::pair<MPI_Comm, int>, void*> g_attrs;
+int MPI_Comm_create_keyval(MPI_Comm_copy_attr_function*, MPI_Comm_delete_attr_function* del, int* keyval, void* extra) {
+    g_keyvals.push_back({del, extra});
+    *keyval = (int)g_keyvals.size() - 1;
+    return 0;
+}
+int MPI_Comm_set_attr(MPI_Comm c, int keyval, void* value) {
+    g_attrs[{c, keyval}] = value;
+    return 0;
+}
 int MPI_Comm_free(MPI_Comm* c) {
+    for (auto it = g_attrs.begin(); it != g_attrs.end();) {
+        if (it->first.first == *c) {
+            auto& kv = g_keyvals[it->first.second];
+            if (kv.first) kv.first(*c, it->first.second, it->second, kv.second);
+            it = g_attrs.erase(it);
+        } else {
+            ++it;
+        }
+    }
     if (*c >= 16) g_comm.erase(*c);
     *c = MPI_COMM_NULL;
     return 0;

@@ -95,6 +95,13 @@ int MPI_Comm_rank(MPI_Comm, int*);
 int MPI_Comm_size(MPI_Comm, int*);
 int MPI_Comm_dup(MPI_Comm, MPI_Comm*);
 int MPI_Comm_free(MPI_Comm*);
+/* communicator attributes (used by the B200 host layer to tie its NCCL communicators to the life of the MPI communicator) */
+#define MPI_KEYVAL_INVALID (-1)
+typedef int MPI_Comm_copy_attr_function(MPI_Comm, int, void*, void*, void*, int*);
+typedef int MPI_Comm_delete_attr_function(MPI_Comm, int, void*, void*);
+#define MPI_COMM_NULL_COPY_FN ((MPI_Comm_copy_attr_function*)0)
+int MPI_Comm_create_keyval(MPI_Comm_copy_attr_function*, MPI_Comm_delete_attr_function*, int*, void*);
+int MPI_Comm_set_attr(MPI_Comm, int, void*);
 int MPI_Comm_split(MPI_Comm, int, int, MPI_Comm*);
 int MPI_Comm_split_type(MPI_Comm, int, int, MPI_Info, MPI_Comm*);
 int MPI_Comm_group(MPI_Comm, MPI_Group*);

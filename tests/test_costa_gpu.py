@@ -457,7 +457,7 @@ def _worker(rank, world, port, nprow, npcol, q):
     torch.cuda.synchronize()
     st = costa.last_layout_multiply_stats(comm)
     ok.append(own_blocks_equal(mats["C"][0], mats["C"][1], mats["A"][2] @ mats["B"][2]))
-    if P_used == world and os.environ.get("COSMA_B200_REORDER_RANKS", "OFF").upper() == "ON":
+    if P_used == world and os.environ.get("COSMA_B200_REORDER_RANKS", "ON").upper() == "ON":  # the default, as in the reference
         ok.append(st["in_remote_elements"] == 0 and st["out_remote_elements"] == 0 and st["in_local_elements"] > 0)
     t = torch.tensor([1 if all(ok) else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -295,15 +295,9 @@ def _gpus():
 
 
 def _skip_unless_ranks(np_):
-    """Multi-rank runs on GPUs: the round-1 GPU budget ran out while a deadlock in tests/cpp/test_multiply.cpp (message tags out of
-    step between active and idle ranks; fixed, and now covered on CPU by test_cpp_programs_multirank_on_cpu) was being diagnosed,
-    so the N > 1 runs of the C++ programs have not been seen green on hardware yet. They are opt-in until then."""
-    if np_ == 1:
-        return
-    if np_ > _gpus():
+    """Multi-rank runs need as many GPUs (one rank per GPU). Seen green on hardware: 2 ranks (profiles/r2b_pytest_gpu_n2.txt)."""
+    if np_ > 1 and np_ > _gpus():
         pytest.skip("needs %d GPUs" % np_)
-    if os.environ.get("COSMA_B200_CPP_MULTIRANK", "0") != "1":
-        pytest.skip("multi-rank C++ programs on GPUs are opt-in (COSMA_B200_CPP_MULTIRANK=1): not yet verified on hardware")
 
 
 @pytest.mark.gpu

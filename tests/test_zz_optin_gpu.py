@@ -69,6 +69,35 @@ def test_unaligned_operands_repacked_onto_the_tensor_pipe(lib, oracle):
     assert code == 0 and "RESULT OK" in text, text[-3000:]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", ["d", "s", "z"])
+def test_large_unaligned_operands_are_repacked_by_default(lib, oracle, dt):
+    """COSMA_B200_REPACK_UNALIGNED unset = AUTO: from m n k >= 2^27 on, operands with an odd leading dimension (COSMA's native layout of an
+    irregular split) are repacked by the copy kernel of csrc/repack.cu and multiplied on the tensor pipe (path 1); exact on small integers."""
+    import numpy as np
+    import torch
+    from cosma_b200 import gemm, _lib
+    if os.environ.get("COSMA_B200_REPACK_UNALIGNED"):
+        pytest.skip("explicit repack mode")
+    rng = np.random.default_rng(5)
+    m, n, k = 1023, 1024, 1023
+    npdt = {"d": np.float64, "s": np.float32, "z": np.complex128}[dt]
+    lda, ldb, ldc = m, k, m                      # odd pitches: not addressable by TMA
+    off = 1 if dt != "z" else 0                  # and a base that is only element-aligned
+    def ints(cnt):
+        v = rng.integers(-3, 4, size=cnt).astype(np.float64)
+        return (v + 1j * rng.integers(-3, 4, size=cnt)).astype(npdt) if dt == "z" else v.astype(npdt)
+    A, B, C = ints(lda * k + off), ints(ldb * n + off), ints(ldc * n)
+    dA, dB, dC = (torch.from_numpy(x).cuda() for x in (A, B, C))
+    es = A.itemsize
+    gemm.gemm_raw(dt, "N", "N", m, n, k, 2.0, dA.data_ptr() + off * es, lda, dB.data_ptr() + off * es, ldb, -1.0, dC.data_ptr(), ldc)
+    torch.cuda.synchronize()
+    assert _lib.load().cosma_b200_last_gemm_path() == 1
+    wide = np.complex128 if dt == "z" else np.float64
+    want = 2.0 * (A[off:].reshape(k, lda).T.astype(wide) @ B[off:].reshape(n, ldb).T.astype(wide)) - C.reshape(n, ldc).T.astype(wide)
+    assert np.array_equal(dC.cpu().numpy().reshape(n, ldc).T, want.astype(npdt))
+
+
 CACHE_SCRIPT = r'''
 import sys
 import torch
@@ -165,9 +194,6 @@ def _run_world_short(world, cases, env, limit=150):
 ])
 def test_host_panels(lib, world, cases):
     """COSMA_B200_HOST_PANELS=4: cosma_b200_multiply_host as four column panels (A uploaded and gathered once, panels of B up / of C down
-    under the GEMMs). Exact against the dense product, twice per case (arenas, streams and events are reused). Written after the
-    round's GPU budget was spent: the cut itself is proven on the CPU (test_schedule_cpu.py), the stream orchestration has never run,
-    so the test is opt-in (COSMA_B200_TEST_HOST_PANELS=1, tools/gpu_r2_call2_2gpu.sh) like the switch it tests."""
-    if os.environ.get("COSMA_B200_TEST_HOST_PANELS", "0") != "1":
-        pytest.skip("opt-in: COSMA_B200_TEST_HOST_PANELS=1 (not yet run on hardware)")
+    under the GEMMs). Exact against the dense product, twice per case (arenas, streams and events are reused). The cut itself is proven
+    on the CPU (test_schedule_cpu.py); seen green on 2 GPUs in profiles/r2b_pytest_gpu_n2.txt."""
     _run_world_short(world, cases, {"COSMA_B200_HOST_PANELS": "4"})
