@@ -183,6 +183,19 @@ int plan_run_overlapped(Plan& plan, const double* alpha, const double* beta, cha
             if (st != COSMA_B200_OK) return st;
         }
     }
+    if (ce) {
+        // Own pieces into their slots of the expanded buffers FIRST, while the device is still empty: an intra-device copy may run as a
+        // kernel, and behind a persistent GEMM that holds every SM it would only start when that GEMM ends (measured at 8 GPUs,
+        // profiles/r2d_bench_n8_default.json: 1.9 ms of the step exposed with the copies queued after the pushes).
+        for (size_t i = 0; i < prog.size(); ++i) {
+            const cosma::MicroOp& o = prog[i];
+            if (o.stream != 1 || o.kind != cosma::MicroKind::ALLGATHER) continue;
+            const auto& op = ops[o.op];
+            const int64_t cnt = op.piece[0][0];
+            CUDA_TRY(cudaMemcpyAsync(arenas[op.matrix] + (op.dst_off + op.my_pos * cnt) * EB, arenas[op.matrix] + op.src_off * EB,
+                                     static_cast<size_t>(cnt * EB), cudaMemcpyDeviceToDevice, comm));
+        }
+    }
     std::vector<int> pending;  // allgathers whose pushes are queued but whose arrival has not been waited for yet
     int last_comm = -1;
     for (size_t i = 0; i < prog.size(); ++i) {
@@ -204,7 +217,6 @@ int plan_run_overlapped(Plan& plan, const double* alpha, const double* beta, cha
                 const char* src = arenas[op.matrix] + op.src_off * EB;
                 st = peer_push(peer, *link, src, static_cast<size_t>(cnt * EB), false, s);
                 if (st != COSMA_B200_OK) return st;
-                CUDA_TRY(cudaMemcpyAsync(arenas[op.matrix] + (op.dst_off + op.my_pos * cnt) * EB, src, static_cast<size_t>(cnt * EB), cudaMemcpyDeviceToDevice, s));
                 pending.push_back(static_cast<int>(i));
                 const bool more = i + 1 < prog.size() && prog[i + 1].stream == 1 && prog[i + 1].kind == cosma::MicroKind::ALLGATHER;
                 if (!more) {
@@ -375,14 +387,16 @@ bool host_panel_pieces(const cosma::Schedule& schedule, int rank, int c, int j, 
     return true;
 }
 
-// COSMA_B200_HOST_PANELS=c (opt-in until it has run on multi-GPU hardware): the host-pointer multiply of a
+// COSMA_B200_HOST_PANELS=c (default 4; seen green on 2 and 8 GPUs, profiles/r2b_pytest_gpu_n2.txt, r2d_bench_n8_panels4.json): the host-pointer multiply of a
 // schedule with collectives as c column panels. A goes up (and is gathered) once; panel j's pieces of B (and of C when beta != 0)
 // travel up on a copy stream while panel j - 1 multiplies, panel j - 1's C travels down on another. Two B / C arena sets alternate.
 // Every decision below depends on global information only (strategy, shapes, c), so all ranks take the same path.
 int host_panels_requested() {
+    // default 4: measured at 8 GPUs on 32768^3 (profiles/r2d_bench_n8_*.json): 206 TFLOP/s end to end against 165 with up-front copies
+    // (device-resident: 290); COSMA_B200_HOST_PANELS=0 | 1 switches the panel pipeline off, c > 1 sets the panel count
     static const int c = [] {
         const char* v = std::getenv("COSMA_B200_HOST_PANELS");
-        const int x = v && *v ? std::atoi(v) : 0;
+        const int x = v && *v ? std::atoi(v) : 4;
         return x > 1 ? x : 0;
     }();
     return c;
@@ -810,7 +824,7 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
         if (!p || !alpha || !beta) return COSMA_B200_INVALID_ARG;
         if (p->schedule.idle()) {
             // idle ranks take part in the one collective of this entry point: the verdict of the arena binding (first call)
-            if (p->overlap_job && !p->owned_bound) {
+            if (p->overlap_job && !p->owned_bound && cosma_b200::host_panels_requested() == 0) {
                 p->owned_bound = true;
                 return cosma_b200_plan_bind_arenas(p, nullptr, nullptr, nullptr, nullptr);
             }
@@ -831,7 +845,9 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
                     return COSMA_B200_OUT_OF_MEMORY;
                 }
             }
-        if (p->overlap_job && !p->owned_bound) {  // the plan's own arenas: copy-engine transport for the overlapped transfers (collective)
+        // the plan's own arenas: copy-engine transport for the overlapped transfers (collective, idle ranks included -- hence a condition
+        // that every rank evaluates alike; with the panel pipeline, the default, the overlapped path is not used from here)
+        if (p->overlap_job && !p->owned_bound && cosma_b200::host_panels_requested() == 0) {
             p->owned_bound = true;
             const int rc = cosma_b200_plan_bind_arenas(p, p->owned[0], p->owned[1], p->owned[2], nullptr);
             if (rc != COSMA_B200_OK) return rc;

@@ -151,9 +151,33 @@ def _random_layout(rng, rows, cols, P, dtype):
     return sim.DistMatrix(rs, cs, owners, P, dtype, "C", pad=int(rng.integers(0, 3)))
 
 
-@pytest.mark.parametrize("P", [3, 4, 6])
+def _relabelling(lib, P, user, native_grids, ta, tb):
+    """The permutation csrc/layout_multiply.cu derives (reference multiply.cpp:136-152): volumes of op(A), op(B) into COSMA's grids
+    and of C out of it, then the matching. user / native_grids: (rowsplit, colsplit, owners) per matrix."""
+    import ctypes
+
+    def ptr(a, t=ctypes.c_int):
+        return a.ctypes.data_as(ctypes.POINTER(t))
+
+    def volume(ga, gb, trans):
+        out = np.zeros(P * P, dtype=np.int64)
+        ga = [np.ascontiguousarray(x, dtype=np.int32).reshape(-1) for x in ga]
+        gb = [np.ascontiguousarray(x, dtype=np.int32).reshape(-1) for x in gb]
+        assert lib.cosma_b200_comm_volume(len(ga[0]) - 1, len(ga[1]) - 1, ptr(ga[0]), ptr(ga[1]), ptr(ga[2]), len(gb[0]) - 1, len(gb[1]) - 1,
+                                          ptr(gb[0]), ptr(gb[1]), ptr(gb[2]), ctypes.c_char(trans.encode()), P, ptr(out, ctypes.c_longlong)) == 0
+        return out.reshape(P, P)
+    total = volume(user[0], native_grids[0], ta) + volume(user[1], native_grids[1], tb) + volume(native_grids[2], user[2], "N")
+    perm = np.zeros(P, dtype=np.int32)
+    flag = ctypes.c_int(0)
+    assert lib.cosma_b200_optimal_reordering(P, ptr(np.ascontiguousarray(total), ctypes.c_longlong), ptr(perm), ctypes.byref(flag)) == 0
+    assert np.array_equal(perm[perm], np.arange(P))  # a matching: always an involution
+    return perm if flag.value else np.arange(P, dtype=np.int32)
+
+
+@pytest.mark.parametrize("relabel", [False, True], ids=["labels_kept", "relabelled"])
+@pytest.mark.parametrize("P", [3, 4, 6, 8])
 @pytest.mark.parametrize("dtype,ta,tb", [("d", "N", "N"), ("d", "T", "N"), ("z", "C", "N"), ("z", "N", "C"), ("d", "T", "T")])
-def test_multiply_using_layout_in_lock_step(lib, oracle, P, dtype, ta, tb):
+def test_multiply_using_layout_in_lock_step(lib, oracle, P, dtype, ta, tb, relabel):
     """cosma::multiply_using_layout (reference multiply.cpp:78-213) END TO END on the CPU with the plans the GPU executes: random block
     layouts with random owners for A, B and C (padded leading dimensions), op(A), op(B) relayouted into COSMA's native layout, the
     compiled schedule, the result relayouted into C's layout with (alpha, beta); exact on integer-valued matrices, real and complex."""
@@ -169,33 +193,43 @@ def test_multiply_using_layout_in_lock_step(lib, oracle, P, dtype, ta, tb):
         dA.scatter(A); dB.scatter(B)
         dC.fill_padding(7)
         dC.scatter(C if beta != 0.0 else np.full_like(C, np.nan))
-        plans = [MultiplyPlan(None, m, n, k, "", dtype, rank=r, nranks=P, allocate=False) for r in range(P)]
-        arenas = [[np.zeros(max(pl.arena_elements[x], 1), dtype=npdt) for x in range(3)] for pl in plans]
-        eb = 8 if dtype == "d" else 16
-        native = []
+        probe = MultiplyPlan(None, m, n, k, "", dtype, rank=0, nranks=P, allocate=False)
+        grids = []
         for x, shape in enumerate(((m, k), (k, n), (m, n))):
-            per_rank = [plans[0].local_blocks("ABC"[x], r) for r in range(P)]
+            per_rank = [probe.local_blocks("ABC"[x], r) for r in range(P)]
             rs = sorted({b[0] for bl in per_rank for b in bl} | {shape[0]})
             cs = sorted({b[2] for bl in per_rank for b in bl} | {shape[1]})
             owners = np.zeros((len(rs) - 1, len(cs) - 1), dtype=np.int32)
             for r, bl in enumerate(per_rank):
                 for (r0, r1, c0, c1) in bl:
                     owners[rs.index(r0), cs.index(c0)] = r
+            grids.append((rs, cs, owners, per_rank))
+        # relabelling as in csrc/layout_multiply.cu: physical rank r plays COSMA rank perm[r]; COSMA rank q is played by perm[q]
+        perm = np.arange(P, dtype=np.int32)
+        if relabel:
+            perm = _relabelling(lib, P, [(d.rowsplit, d.colsplit, d.owners) for d in (dA, dB, dC)], [g[:3] for g in grids], ta, tb)
+        probe.destroy()
+        plans = [MultiplyPlan(None, m, n, k, "", dtype, rank=int(perm[r]), nranks=P, allocate=False) for r in range(P)]
+        arenas = [[np.zeros(max(pl.arena_elements[x], 1), dtype=npdt) for x in range(3)] for pl in plans]
+        eb = 8 if dtype == "d" else 16
+        native = []
+        for x, (rs, cs, owners, per_rank) in enumerate(grids):
             lays = []
             for r in range(P):
                 blocks, pos = [], 0
-                for (r0, r1, c0, c1) in per_rank[r]:
+                for (r0, r1, c0, c1) in per_rank[perm[r]]:
                     nr, nc = r1 - r0 + 1, c1 - c0 + 1
                     blocks.append((rs.index(r0), cs.index(c0), arenas[r][x].ctypes.data + pos * eb, nr))
                     pos += nr * nc
-                lays.append(costa.custom_layout(rs, cs, owners, blocks, "C"))
+                lays.append(costa.custom_layout(rs, cs, perm[owners], blocks, "C"))
             native.append(lays)
         tin = []
         for r in range(P):
             tp = costa.TransformPlan(None, dtype, [(dA.layout(r), native[0][r], ta, 1.0, 0.0), (dB.layout(r), native[1][r], tb, 1.0, 0.0)], rank=r, nranks=P)
             tin.append(tp.export()); tp.destroy()
         sim.simulate(oracle, dtype, tin, [(1.0, 0.0), (1.0, 0.0)])
-        schedule_sim.run_schedules(plans, arenas, 1.0, 0.0)
+        inv = np.argsort(perm)  # the schedules are indexed by COSMA rank
+        schedule_sim.run_schedules([plans[inv[q]] for q in range(P)], [arenas[inv[q]] for q in range(P)], 1.0, 0.0)
         tout = []
         for r in range(P):
             tp = costa.TransformPlan(None, dtype, [(native[2][r], dC.layout(r), "N", alpha, beta)], rank=r, nranks=P)
