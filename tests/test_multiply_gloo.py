@@ -131,3 +131,97 @@ def test_two_process_gloo(lib, m, n, k, steps, beta):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+# ---- the overlapped schedules (include/cosma/overlap.hpp) across real processes ---------------------------------------------
+
+def _worker_overlapped(rank, world, port, m, n, k, steps, alpha, beta, zero_sm, out_q):
+    """Every process interprets ITS micro-op program (MultiplyPlan.overlap(): GEMM panels, allgathers, the exchange of the partial C
+    halves, accumulations) in program order -- a valid serialisation of its two streams -- with gloo point-to-point messages where
+    the device executor pushes through copy engines / NCCL."""
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["COSMA_OVERLAP_COMM_AND_COMP"] = "FORCE"
+    os.environ["COSMA_B200_OVERLAP_GRANULE"] = "8"
+    if zero_sm:
+        os.environ["COSMA_B200_OVERLAP_ZERO_SM"] = "ON"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cosma_b200.distributed import MultiplyPlan, fill_local_from_global, gather_local_to_global
+    from schedule_sim import micro_gemm_cpu
+    rng = np.random.default_rng(9)
+    Ag = rng.integers(0, 10, size=(m, k)).astype(np.float64)
+    Bg = rng.integers(0, 10, size=(k, n)).astype(np.float64)
+    Cg = rng.integers(0, 10, size=(m, n)).astype(np.float64)
+    pl = MultiplyPlan(None, m, n, k, steps, "d", rank=rank, nranks=world, allocate=False)
+    ov = pl.overlap()
+    assert ov["enabled"], ov["why"]
+    sched = pl.ops()
+    arenas = [np.full(max(pl.arena_elements[x], 1), np.nan) for x in range(3)]   # poisoned: nothing is read before it arrives
+    for x, (label, full) in enumerate((("A", Ag), ("B", Bg), ("C", Cg if beta != 0 else np.full_like(Cg, np.nan)))):
+        arenas[x][:pl.initial_elements[x]] = 0.0
+        fill_local_from_global(pl, label, arenas[x], full)
+    bt = lambda mode: {0: 0.0, 1: 1.0, 2: beta}[mode]
+    for o in ov["ops"]:
+        if o["kind"] == "gemm":
+            micro_gemm_cpu(o, *arenas, alpha, beta)
+        elif o["kind"] == "accumulate":
+            b = bt(o["beta"])
+            if not (o["beta_term"] and b == 0):
+                C = arenas[2]
+                C[o["dst_off"]:o["dst_off"] + o["count"]] = b * C[o["dst_off"]:o["dst_off"] + o["count"]] + C[o["add_off"]:o["add_off"] + o["count"]]
+        elif o["kind"] == "allgather":
+            op = sched[o["op"]]
+            assert op["regular"] and len(op["ring"]) == 2
+            buf, me, cnt = arenas[op["matrix"]], op["my_pos"], op["piece"][0][0]
+            mine = buf[op["src_off"]:op["src_off"] + cnt].copy()
+            got = _exchange(op["ring"], me, [mine if g != me else None for g in range(2)], [np.empty(cnt) if g != me else None for g in range(2)])
+            buf[op["dst_off"] + me * cnt:op["dst_off"] + (me + 1) * cnt] = mine
+            buf[op["dst_off"] + (1 - me) * cnt:op["dst_off"] + (2 - me) * cnt] = got[1 - me]
+        elif o["kind"] == "exchange":
+            ring = next(s["ring"] for s in sched if s["kind"] != "gemm" and s["ring_index"] == o["ring_index"])
+            me = 1 - o["peer"]
+            C = arenas[2]
+            send = C[o["send_off"]:o["send_off"] + o["count"]].copy()
+            got = _exchange(ring, me, [send if g != me else None for g in range(2)], [np.empty(o["count"]) if g != me else None for g in range(2)])
+            at = o["recv_off_zero"] if bt(o["beta"]) == 0 else o["recv_off"]
+            C[at:at + o["count"]] = got[o["peer"]]
+        else:
+            raise AssertionError("serial collectives are not part of these cases: %s" % o)
+    mine = torch.from_numpy(arenas[2][:max(pl.initial_elements[2], 1)].copy())
+    if rank == 0:
+        full = np.zeros((m, n))
+        for r in range(pl.P_used):
+            if r == 0:
+                loc = mine.numpy()
+            else:
+                cnt = sum((b[1] - b[0] + 1) * (b[3] - b[2] + 1) for b in pl.local_blocks("C", r))
+                t = torch.empty(max(cnt, 1), dtype=torch.float64)
+                dist.recv(t, src=r)
+                loc = t.numpy()
+            gather_local_to_global(pl, "C", loc, full, rank=r)
+        want = alpha * (Ag @ Bg) + beta * Cg
+        out_q.put(bool(np.array_equal(full, want)))
+    else:
+        dist.send(mine, dst=0)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,m,n,k,steps,beta,zero_sm", [
+    (2, 64, 64, 64, "pk2", 2.0, False), (2, 64, 64, 64, "pk2", 0.0, True), (2, 64, 96, 64, "pm2", 1.0, True), (2, 96, 64, 64, "pn2", 0.0, False),
+    (4, 128, 128, 128, "pn2,pk2", 0.0, True), (4, 128, 128, 128, "pm2,pn2", 1.0, False),
+])
+def test_overlapped_program_across_processes(lib, world, m, n, k, steps, beta, zero_sm):
+    """zero_sm: the panel shapes of the copy-engine transport (no narrow launch), else those of the NCCL transport."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlapped, args=(r, world, port, m, n, k, steps, 2.0, beta, zero_sm, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
