@@ -112,6 +112,37 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+class Watchdog:
+    """A stage that never returns (a collective some rank does not join, a wedged device) must not cost the line: once the deadline has
+    passed, rank 0 prints what has been measured so far -- the headline measurement comes first, the extras (`e2e`, `parity`, `also`,
+    `cpu_baseline`) after it -- with the unfinished stage named under "incomplete", and every rank leaves. Never fires in a healthy run
+    (N = 1 takes about 100 s, N = 8 about 60 s). COSMA_B200_BENCH_DEADLINE_S overrides the limit; 0 switches the watchdog off."""
+
+    def __init__(self, rank):
+        self.rank, self.line, self.stage, self.t0, self.printed = rank, None, "start-up", time.time(), False
+        try:
+            self.deadline = float(os.environ.get("COSMA_B200_BENCH_DEADLINE_S", "600"))
+        except ValueError:
+            self.deadline = 600.0
+        if self.deadline > 0:
+            t = threading.Timer(self.deadline + (0.0 if rank == 0 else 5.0), self.fire)
+            t.daemon = True
+            t.start()
+
+    def elapsed(self):
+        return time.time() - self.t0
+
+    def fire(self):
+        if self.rank == 0 and not self.printed:  # (printed: only the teardown hangs -- the line is out, leave quietly)
+            line = dict(self.line) if self.line else {"metric": METRIC, "value": None, "unit": "TFLOP/s"}
+            line["incomplete"] = "stage '%s' had not finished %d s after start; the line holds what was measured before it" % (self.stage, int(self.deadline))
+            try:
+                print(json.dumps(line), flush=True)
+            except Exception:
+                pass
+        os._exit(0 if (self.rank != 0 or self.line or self.printed) else 3)
+
+
 def gemm_peak(dtype):
     """Roofline denominator of the local GEMM kernels, per GPU. FP64 (d, z): MEASURED_PEAKS.json (driver-written) carries no FP64 figure,
     so the larger of this repo's own DMMA issue-rate probe on the same pool (profiles/FP64_PEAK.json, 37.0) and the nominal
@@ -292,7 +323,8 @@ class Env:
         return t.item()
 
 
-def run_multiply(env, m, n, k, dtype, steps, warmup, strategy="", with_e2e=True, with_parity=True, sample_clocks=False, comm=None):
+def run_multiply(env, m, n, k, dtype, steps, warmup, strategy="", with_e2e=True, with_parity=True, sample_clocks=False, comm=None,
+                 on_measured=None, stage=None):
     """One multiply workload: W warm-up steps, K timed steps (device events, max over ranks), roofline of the GEMM launches, collectives,
     end to end from pinned host memory, and an exact parity check on integer-valued operands. -> dict of results."""
     torch = env.torch
@@ -343,12 +375,17 @@ def run_multiply(env, m, n, k, dtype, steps, warmup, strategy="", with_e2e=True,
             out["collectives"] = job.collectives(last_step_ms)  # rank 0's last timed step
         except Exception as e:  # a reporting extra must never cost the bench line
             out["collectives"] = {"error": str(e)[:300]}
+    if on_measured:
+        on_measured(out)  # the device-resident measurement is complete: from here on the watchdog has a line to print
+    stage = stage or (lambda name: None)
     if with_e2e:
+        stage("e2e")
         try:
             out["e2e"] = job.e2e(max(2, min(steps, 3)))
         except Exception as e:  # an error every rank sees (e.g. out of pinned memory) must not cost the device-resident line
             out["e2e"] = {"error": str(e)[:300]}
     if with_parity:
+        stage("parity")
         try:
             out["parity"] = job.parity()
         except Exception as e:
@@ -445,6 +482,7 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    dog = Watchdog(int(os.environ.get("RANK", "0")))
     env = Env()
     from cosma_b200 import _lib
     from cosma_b200.distributed import init_comm
@@ -468,9 +506,35 @@ def main():
             env.dist.destroy_process_group()
         return 0
 
-    res = run_multiply(env, m, n, k, dtype, args.steps, args.warmup, strategy=args.strategy, with_e2e=not args.no_e2e,
-                       with_parity=not args.no_parity, sample_clocks=True, comm=comm)
     peak, _ = gemm_peak(dtype)
+    eb = 8 if dtype == "d" else (16 if dtype == "z" else (4 if dtype == "s" else 8))
+
+    def assemble(res):
+        """The bench line from the results measured so far (built again as the extras complete; key order as in the contract)."""
+        line = {"metric": METRIC, "value": res["value"], "unit": "TFLOP/s", "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE_NAME[dtype],
+                "data": "synthetic",
+                "config": {"workload": name, "m": m, "n": n, "k": k, "strategy": res["strategy"], "alpha": 1, "beta": 0,
+                           "l2": "inputs larger than L2 (A+B+C = %.1f GB per job vs 126 MB L2)" % (eb * 1e-9 * (m * k + k * n + m * n)),
+                           "peak_per_gpu_tflops": peak, "frac_of_peak": res["value"] / (peak * env.world)},
+                "roofline": res["roofline"], "cpu_baseline": res.get("cpu_baseline"), "e2e": res.get("e2e"), "gpu_launches": res["launches"],
+                "clocks": res.get("clocks"), "parity": res.get("parity")}
+        if env.affinity is not None:
+            line["config"]["host_affinity_rank0"] = env.affinity
+        if "collectives" in res:
+            line["collectives"] = res["collectives"]  # rank 0's last timed step
+        if res.get("also"):
+            line["also"] = dict(res["also"])
+        dog.line = line  # one reference assignment: the watchdog thread sees the old line or the new one, never half of one
+        return line
+
+    def stage(name):
+        dog.stage = name
+
+    stage("device-resident measurement of %s" % args.workload)
+    res = run_multiply(env, m, n, k, dtype, args.steps, args.warmup, strategy=args.strategy, with_e2e=not args.no_e2e,
+                       with_parity=not args.no_parity, sample_clocks=True, comm=comm, on_measured=assemble, stage=stage)
+    assemble(res)
 
     # the other named configs that fit this job, in short (2 timed steps each): visible in the driver's records
     also = {}
@@ -481,39 +545,36 @@ def main():
         if env.world == 8:
             extra += ["largek", "pzgemm"]
         for w in extra:
+            stage("also." + w)
+            if dog.deadline > 0 and env.max_over_ranks(dog.elapsed()) > 0.5 * dog.deadline:  # (one verdict for all ranks: the extras are collective)
+                also[w] = {"skipped": "more than half of the run's time limit was used before this extra"}
+                res["also"] = also
+                continue
             try:
                 if w == "pzgemm":
                     also[w] = run_pzgemm(env, 2, 2, comm, with_e2e=False)
                 else:
                     wm, wn, wk, wd, wname = WORKLOADS[w]
-                    r = run_multiply(env, wm, wn, wk, wd, 2, 2, with_e2e=(w == "cfg2"), with_parity=(w != "cfg2"), comm=comm)
+                    r = run_multiply(env, wm, wn, wk, wd, 2, 2, with_e2e=(w == "cfg2"), with_parity=(w != "cfg2"), comm=comm, stage=stage)
                     wpeak, _ = gemm_peak(wd)
                     also[w] = {"workload": wname % env.world, "value": r["value"], "unit": "TFLOP/s", "ms_per_step": r["ms_per_step"],
                                "strategy": r["strategy"], "frac_of_peak": r["value"] / (wpeak * env.world), "roofline": r["roofline"],
                                "collectives": r.get("collectives"), "e2e": r.get("e2e"), "parity": r.get("parity"), "steps": 2, "warmup": 2}
             except Exception as e:
                 also[w] = {"error": str(e)[:300]}
+            res["also"] = also
+            assemble(res)
 
     if env.rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline and dtype == "d":
-            cpu = cpu_baseline(m, n, k)
-        eb = 8 if dtype == "d" else (16 if dtype == "z" else (4 if dtype == "s" else 8))
-        line = {"metric": METRIC, "value": res["value"], "unit": "TFLOP/s", "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE_NAME[dtype],
-                "data": "synthetic",
-                "config": {"workload": name, "m": m, "n": n, "k": k, "strategy": res["strategy"], "alpha": 1, "beta": 0,
-                           "l2": "inputs larger than L2 (A+B+C = %.1f GB per job vs 126 MB L2)" % (eb * 1e-9 * (m * k + k * n + m * n)),
-                           "peak_per_gpu_tflops": peak, "frac_of_peak": res["value"] / (peak * env.world)},
-                "roofline": res["roofline"], "cpu_baseline": cpu, "e2e": res.get("e2e"), "gpu_launches": res["launches"], "clocks": res.get("clocks"),
-                "parity": res.get("parity")}
-        if env.affinity is not None:
-            line["config"]["host_affinity_rank0"] = env.affinity
-        if "collectives" in res:
-            line["collectives"] = res["collectives"]  # rank 0's last timed step
-        if also:
-            line["also"] = also
-        print(json.dumps(line))
+        # rank 0 at N = 1 only (the contract): at N > 1 the reference arm (--impl reference) gives the CPU number of the same job
+        if not args.no_cpu_baseline and dtype == "d" and env.world == 1:
+            stage("cpu_baseline")
+            res["cpu_baseline"] = cpu_baseline(m, n, k)
+        line = assemble(res)
+        stage("printing")
+        print(json.dumps(line), flush=True)
+        dog.printed = True
+    stage("teardown")
     comm.destroy()
     if env.world > 1:
         env.dist.destroy_process_group()

@@ -67,6 +67,7 @@ struct Plan {
     cosma::OverlapProgram overlap;
     bool overlap_job = false;  // every active rank of the job lowers (the same value on every rank, idle ones included)
     int reserved = 0;
+    bool rings_capped = false;  // the ring communicators were split with maxCTAs = reserved (NCCL transport of the overlapped program)
     cudaStream_t comm_stream = nullptr;
     std::vector<cudaEvent_t> micro_ev;  // [2 * micro-op] start / end, + 1 entry event
     bool last_run_overlapped = false;

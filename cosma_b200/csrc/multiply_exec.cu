@@ -301,8 +301,16 @@ int plan_run(Plan& plan, const double* alpha, const double* beta, void* A_, void
     plan.last_launches = 0;
     plan.last_run_overlapped = false;
     if (plan.overlap.enabled && !host && skip_allgather_mask == 0) {
-        plan.last_run_overlapped = true;
-        return plan_run_overlapped(plan, alpha, beta, arenas, stream);
+        // Transports of the overlapped program: copy engines when these arenas are bound (the default), else NCCL kernels beside narrow
+        // GEMMs -- which needs ring communicators limited to the SMs those GEMMs leave free (rings_capped: COSMA_B200_PEER_COPY=OFF
+        // at plan creation). With neither, the serial schedule is the better one. The arenas are bound collectively and the verdict is
+        // shared, so every rank of a ring decides alike.
+        bool bound = false;
+        for (const auto& t : plan.peers) bound |= t->ready && A == t->bound[0] && B == t->bound[1] && C == t->bound[2];
+        if (bound || plan.rings_capped) {
+            plan.last_run_overlapped = true;
+            return plan_run_overlapped(plan, alpha, beta, arenas, stream);
+        }
     }
     // with timing on, every op (GEMM, allgather, reduce) is bracketed by a pair of events: ev[2*i], ev[2*i+1] for op i
     if (plan.time_gemms) {
@@ -659,7 +667,11 @@ static int plan_create_impl(void* comm, int rank, int nranks, int m, int n, int 
                 plan->overlap = cosma::OverlapProgram();
                 plan->overlap.why = !why.empty() ? why : (!tuning.enabled ? "switched off (COSMA_OVERLAP_COMM_AND_COMP)" : "not a multi-rank schedule of at most 64 ranks");
             }
-            use_ring_config = all;
+            // Only the NCCL transport of the overlapped program needs capped rings. With the copy-engine transport (the default) the rings
+            // carry the SERIAL collectives -- the host-pointer paths (column panels, streamed operands) and rings larger than two --
+            // and those want every channel NCCL can use: 8 CTAs move ~89 GB/s (profiles/r2b_bench_n2_*.json) against 460-490 uncapped.
+            use_ring_config = all && !cosma_b200::peer_copy_enabled();
+            plan->rings_capped = use_ring_config;
             plan->overlap_job = all;
         }
         plan->parent = c;

@@ -45,3 +45,37 @@ def test_host_affinity_helper_is_best_effort():
     if not info["bound"]:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+WATCHDOG_SCRIPT = r"""
+import json, os, sys, time
+sys.path.insert(0, %r)
+import bench
+dog = bench.Watchdog(int(os.environ["RANK"]))
+mode = sys.argv[1]
+if mode == "measured":      # the headline measurement is in, an extra never returns
+    dog.line = {"metric": bench.METRIC, "value": 1.5, "unit": "TFLOP/s"}
+    dog.stage = "also.pzgemm"
+elif mode == "printed":     # the line is out, the teardown never returns
+    print(json.dumps({"value": 2.5}), flush=True)
+    dog.printed = True
+    dog.stage = "teardown"
+time.sleep(60)
+"""
+
+
+@pytest.mark.parametrize("mode,rank,rc,lines", [("measured", 0, 0, 1), ("nothing", 0, 3, 1), ("printed", 0, 0, 1), ("measured", 1, 0, 0)])
+def test_bench_watchdog(mode, rank, rc, lines):
+    """bench.Watchdog: a stage that never returns costs the extras, not the line -- rank 0 prints what was measured (exit 0), or an
+    explicit value-less line when nothing was (exit 3); after the line is out it leaves quietly; other ranks never print."""
+    env = dict(os.environ, RANK=str(rank), COSMA_B200_BENCH_DEADLINE_S="1")
+    out = subprocess.run([sys.executable, "-c", WATCHDOG_SCRIPT % ROOT, mode], capture_output=True, text=True, timeout=50, env=env, cwd=ROOT)
+    assert out.returncode == rc, (out.returncode, out.stderr[-1000:])
+    got = [json.loads(ln) for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(got) == lines, out.stdout
+    if mode == "measured" and rank == 0:
+        assert got[0]["value"] == 1.5 and "also.pzgemm" in got[0]["incomplete"]
+    if mode == "nothing":
+        assert got[0]["value"] is None and "start-up" in got[0]["incomplete"]
+    if mode == "printed":
+        assert got[0] == {"value": 2.5}
