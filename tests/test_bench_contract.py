@@ -79,3 +79,66 @@ def test_bench_watchdog(mode, rank, rc, lines):
         assert got[0]["value"] is None and "start-up" in got[0]["incomplete"]
     if mode == "printed":
         assert got[0] == {"value": 2.5}
+
+
+def test_our_arm_assembles_the_line_stage_by_stage(monkeypatch, capsys):
+    """bench.main() of our arm with the GPU work stubbed out: the line exists (for the watchdog) as soon as the device-resident
+    measurement is in, gains e2e / parity / also as they complete, and is printed once with the contract's keys."""
+    import bench
+    from cosma_b200 import _lib
+    _lib.load()
+    seen = []
+
+    class FakeEnv:
+        world, rank, local_rank, dev, affinity, dist = 1, 0, 0, None, None, None
+
+        def barrier(self):
+            pass
+
+        def max_over_ranks(self, x):
+            return x
+
+    def fake_run_multiply(env, m, n, k, dtype, steps, warmup, strategy="", with_e2e=True, with_parity=True, sample_clocks=False, comm=None,
+                          on_measured=None, stage=None):
+        out = {"strategy": "", "ms_per_step": 2.0, "value": 2.0 * m * n * k / 2e-3 * 1e-12, "launches": steps,
+               "roofline": {"bound": "tensor", "achieved": 1.0, "peak": 2.0, "unit": "TFLOP/s", "frac": 0.5, "traffic": None}}
+        if on_measured:
+            on_measured(out)
+            seen.append(dict(dog_line()))
+        if with_e2e:
+            out["e2e"] = {"value": 1.0, "unit": "TFLOP/s", "h2d_bytes_per_step": 8 * (m * k + k * n), "d2h_bytes_per_step": 8 * m * n}
+        if with_parity:
+            out["parity"] = {"ok": True, "exact": True}
+        return out
+
+    dogs = []
+    real_dog = bench.Watchdog
+
+    def make_dog(rank):
+        os.environ["COSMA_B200_BENCH_DEADLINE_S"] = "0"  # no timer in the test process
+        d = real_dog(rank)
+        dogs.append(d)
+        return d
+
+    def dog_line():
+        return dogs[0].line
+
+    monkeypatch.setattr(bench, "Env", FakeEnv)
+    monkeypatch.setattr(bench, "run_multiply", fake_run_multiply)
+    monkeypatch.setattr(bench, "Watchdog", make_dog)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "1", "--steps", "4", "--warmup", "3", "--no-cpu-baseline"])
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    try:
+        assert bench.main() == 0
+    finally:
+        os.environ.pop("COSMA_B200_BENCH_DEADLINE_S", None)
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    need = (KEYS - {"impl"}) | {"roofline", "parity", "clocks", "also"}
+    assert need <= set(d), sorted(need - set(d))
+    assert d["n_gpus"] == 1 and d["steps"] == 4 and d["warmup"] == 3 and d["config"]["m"] == 32768 and d["gpu_launches"] == 4
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["parity"]["ok"] and d["also"]["cfg2"]["e2e"]["value"] == 1.0
+    # what the watchdog would have printed had the e2e stage of the headline workload never returned
+    assert seen[0]["value"] == d["value"] and seen[0]["e2e"] is None and "also" not in seen[0]
+    assert dogs[0].printed and dogs[0].stage == "teardown"
