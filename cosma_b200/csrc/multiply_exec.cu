@@ -913,8 +913,8 @@ int cosma_b200_multiply_host(void* plan, const double* alpha, const double* beta
 /* Binds the device arenas the plan will be run on (collective over the plan's communicator: every rank calls it, idle ranks too). An
  * overlapped plan (cosma_b200_plan_overlap_export) then moves its ring-of-two transfers with COPY ENGINES straight into the ring
  * mates' arenas (CUDA IPC) instead of NCCL kernels, and re-plans its panels for a device that no longer shares SMs with communication.
- * *active = 1 when that transport is in place (on every rank alike); 0: nothing changes (plan not overlapped, COSMA_B200_PEER_COPY=OFF,
- * or some rank could not map its mate's memory). cosma_b200_multiply must then be called with exactly these arenas. */
+ * *active = 1 when that transport is in place (on every rank alike); 0: plan not overlapped, COSMA_B200_PEER_COPY=OFF (overlap over NCCL),
+ * or some rank could not map its mate's memory (serial schedule). cosma_b200_multiply must then be called with exactly these arenas. */
 int cosma_b200_plan_bind_arenas(void* plan, void* A, void* B, void* C, int* active) {
     return guarded("cosma_b200_plan_bind_arenas", [&]() -> int {
         Plan* p = static_cast<Plan*>(plan);

@@ -144,8 +144,9 @@ COSMA_B200_API int cosma_b200_plan_overlap_export(void* plan, int64_t* buf, int6
 /* Binds the DEVICE arenas the plan will run on -- collective over the plan's communicator, idle ranks included. An overlapped plan then
  * moves its ring-of-two transfers with copy engines straight into the ring mates' arenas (CUDA IPC mappings, ordered by stream memory
  * operations on epoch flags: no SM is spent on communication) and re-plans its GEMM panels for the whole device. *active = 1 when that
- * transport is in place (every rank alike); 0: nothing changes (plan not overlapped, COSMA_B200_PEER_COPY=OFF, or a rank could not map
- * its mate's memory: the plan keeps NCCL). cosma_b200_multiply must afterwards be called with exactly these arenas. The library binds
+ * transport is in place (every rank alike); 0: plan not overlapped, COSMA_B200_PEER_COPY=OFF (the overlapped transfers stay NCCL kernels
+ * beside narrow GEMMs), or a rank could not map its mate's memory (the plan then runs its serial schedule over NCCL, as it does on
+ * arenas that were never bound). cosma_b200_multiply must afterwards be called with exactly these arenas. The library binds
  * the arenas it owns itself (cosma_b200_multiply_host, ?multiply_using_layout, p?gemm). */
 COSMA_B200_API int cosma_b200_plan_bind_arenas(void* plan, void* A, void* B, void* C, int* active);
 
