@@ -67,6 +67,14 @@ def workload(args):
     return name, m, n, k, dtype
 
 
+def workload_config(name, m, n, k, strategy, dtype):
+    """The `config` of the line: what the workload IS -- the same dict in our arm and in the reference arm, which times the reference's CPU
+    COSMA on this very config (a bounded sample of it, described under cpu_baseline.sample). Nothing value-dependent goes in here."""
+    eb = 8 if dtype == "d" else (16 if dtype == "z" else (4 if dtype == "s" else 8))
+    return {"workload": name, "m": m, "n": n, "k": k, "strategy": strategy, "alpha": 1, "beta": 0,
+            "l2": "inputs larger than L2 (A+B+C = %.1f GB per job vs 126 MB L2)" % (eb * 1e-9 * (m * k + k * n + m * n))}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -217,7 +225,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "m": m, "n": n, "k": k, "sample": sample},
+            "config": workload_config(name, m, n, k, args.strategy or orc.ref_strategy(m, n, k, max(1, args.gpus))[0], dtype),
             "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -253,12 +261,12 @@ def reference_arm_ranks(args, name, m, n, k, ks, reps, cores):
     timed = sorted(times)[:args.steps]  # the miniapp reports its repetitions sorted: keep the K fastest of W + K
     ms = sum(timed) / len(timed)
     tf = 2.0 * m * n * ks / (ms * 1e-3) * 1e-12
-    sample = ("reference cosma_miniapp on %d minimpi ranks x %d OpenBLAS 0.3.30 threads, m=%d n=%d k=%d (k cut from %d), strategy [%s], "
+    sample = ("reference cosma_miniapp on %d minimpi ranks x %d OpenBLAS 0.3.30 threads, m=%d n=%d k=%d (k cut from %d), strategy of the sample [%s], "
               "mean of the %d fastest of %d repetitions" % (R, threads, m, n, ks, k, "; ".join(steps), len(timed), reps))
     line = {"impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "m": m, "n": n, "k": k, "sample": sample},
+            "config": workload_config(name, m, n, k, args.strategy or orc.ref_strategy(m, n, k, R)[0], "d"),
             "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": threads * R, "kind": "reference", "sample": sample},
             "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -507,20 +515,16 @@ def main():
         return 0
 
     peak, _ = gemm_peak(dtype)
-    eb = 8 if dtype == "d" else (16 if dtype == "z" else (4 if dtype == "s" else 8))
 
     def assemble(res):
         """The bench line from the results measured so far (built again as the extras complete; key order as in the contract)."""
         line = {"metric": METRIC, "value": res["value"], "unit": "TFLOP/s", "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE_NAME[dtype],
-                "data": "synthetic",
-                "config": {"workload": name, "m": m, "n": n, "k": k, "strategy": res["strategy"], "alpha": 1, "beta": 0,
-                           "l2": "inputs larger than L2 (A+B+C = %.1f GB per job vs 126 MB L2)" % (eb * 1e-9 * (m * k + k * n + m * n)),
-                           "peak_per_gpu_tflops": peak, "frac_of_peak": res["value"] / (peak * env.world)},
-                "roofline": res["roofline"], "cpu_baseline": res.get("cpu_baseline"), "e2e": res.get("e2e"), "gpu_launches": res["launches"],
+                "data": "synthetic", "config": workload_config(name, m, n, k, res["strategy"], dtype),
+                "peak_per_gpu_tflops": peak, "frac_of_peak": res["value"] / (peak * env.world), "roofline": res["roofline"], "cpu_baseline": res.get("cpu_baseline"), "e2e": res.get("e2e"), "gpu_launches": res["launches"],
                 "clocks": res.get("clocks"), "parity": res.get("parity")}
         if env.affinity is not None:
-            line["config"]["host_affinity_rank0"] = env.affinity
+            line["host_affinity_rank0"] = env.affinity
         if "collectives" in res:
             line["collectives"] = res["collectives"]  # rank 0's last timed step
         if res.get("also"):

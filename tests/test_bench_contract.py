@@ -25,6 +25,10 @@ def test_reference_arm_line(ref, gpus):
     assert d["impl"] == "reference" and d["n_gpus"] == gpus and d["unit"] == "TFLOP/s" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the reference arm runs on OUR arm's config: the very dict bench.workload_config gives our line (the sample it times is described
+    # under cpu_baseline.sample); the strategy is the reference's own Strategy(m, n, k, P), which the planning tests pin equal to ours
+    import bench
+    assert d["config"] == bench.workload_config("dgemm m=768 n=640 k=512 (override)", 768, 640, 512, {1: "", 2: "pm2"}[gpus], "d"), d["config"]
 
 
 def test_other_ranks_of_the_reference_arm_do_nothing(ref):
@@ -138,6 +142,7 @@ def test_our_arm_assembles_the_line_stage_by_stage(monkeypatch, capsys):
     need = (KEYS - {"impl"}) | {"roofline", "parity", "clocks", "also"}
     assert need <= set(d), sorted(need - set(d))
     assert d["n_gpus"] == 1 and d["steps"] == 4 and d["warmup"] == 3 and d["config"]["m"] == 32768 and d["gpu_launches"] == 4
+    assert d["config"] == bench.workload_config(bench.WORKLOADS["cfg3"][4] % 1, 32768, 32768, 32768, "", "d") and d["frac_of_peak"] > 0 and "peak_per_gpu_tflops" in d
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["parity"]["ok"] and d["also"]["cfg2"]["e2e"]["value"] == 1.0
     # what the watchdog would have printed had the e2e stage of the headline workload never returned
     assert seen[0]["value"] == d["value"] and seen[0]["e2e"] is None and "also" not in seen[0]
