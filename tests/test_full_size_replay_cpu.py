@@ -24,7 +24,7 @@ def big_b():
 
 
 @pytest.mark.parametrize("P,transport,beta,alpha", [(2, "copy_engine", 0.0, 1.0), (4, "copy_engine", 0.0, 1.0), (8, "copy_engine", 0.0, 1.0),
-                                                    (4, "copy_engine", -1.0, 2.0), (4, "nccl", 2.0, 1.0), (8, "serial", 0.0, 1.0)])
+                                                    (4, "copy_engine", -1.0, 2.0), (4, "nccl", 2.0, 1.0)])
 def test_bench_programs_replayed(lib, monkeypatch, big_b, P, transport, beta, alpha):
     for v in ("COSMA_OVERLAP_COMM_AND_COMP", "COSMA_B200_OVERLAP_GRANULE", "COSMA_B200_OVERLAP_SMS", "COSMA_B200_OVERLAP_GBPS", "COSMA_B200_OVERLAP_ZERO_SM"):
         monkeypatch.delenv(v, raising=False)
