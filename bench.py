@@ -124,14 +124,16 @@ class Watchdog:
     """A stage that never returns (a collective some rank does not join, a wedged device) must not cost the line: once the deadline has
     passed, rank 0 prints what has been measured so far -- the headline measurement comes first, the extras (`e2e`, `parity`, `also`,
     `cpu_baseline`) after it -- with the unfinished stage named under "incomplete", and every rank leaves. Never fires in a healthy run
-    (N = 1 takes about 100 s, N = 8 about 60 s). COSMA_B200_BENCH_DEADLINE_S overrides the limit; 0 switches the watchdog off."""
+    (N = 1 takes about 100 s, N = 8 about 60 s with the driver's 20 + 5 steps; the limit is 600 s, more when more steps are asked for).
+    COSMA_B200_BENCH_DEADLINE_S overrides the limit; 0 switches the watchdog off."""
 
-    def __init__(self, rank):
+    def __init__(self, rank, reps=0):
         self.rank, self.line, self.stage, self.t0, self.printed = rank, None, "start-up", time.time(), False
+        default = max(600.0, 150.0 + 4.0 * reps)  # a run asked for many steps gets the time they need (a step is ~2 s at N = 1)
         try:
-            self.deadline = float(os.environ.get("COSMA_B200_BENCH_DEADLINE_S", "600"))
+            self.deadline = float(os.environ.get("COSMA_B200_BENCH_DEADLINE_S", default))
         except ValueError:
-            self.deadline = 600.0
+            self.deadline = default
         if self.deadline > 0:
             t = threading.Timer(self.deadline + (0.0 if rank == 0 else 5.0), self.fire)
             t.daemon = True
@@ -490,7 +492,7 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
-    dog = Watchdog(int(os.environ.get("RANK", "0")))
+    dog = Watchdog(int(os.environ.get("RANK", "0")), args.steps + args.warmup)
     env = Env()
     from cosma_b200 import _lib
     from cosma_b200.distributed import init_comm

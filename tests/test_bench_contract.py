@@ -118,9 +118,9 @@ def test_our_arm_assembles_the_line_stage_by_stage(monkeypatch, capsys):
     dogs = []
     real_dog = bench.Watchdog
 
-    def make_dog(rank):
+    def make_dog(rank, reps=0):
         os.environ["COSMA_B200_BENCH_DEADLINE_S"] = "0"  # no timer in the test process
-        d = real_dog(rank)
+        d = real_dog(rank, reps)
         dogs.append(d)
         return d
 
