@@ -250,3 +250,27 @@ def test_column_panels_randomised(lib, seed):
         for pl in full + (sub or []):
             pl.destroy()
     assert checked >= 1
+
+
+def test_host_panel_pipeline_applies_at_the_bench_shapes(lib):
+    """32768^3 on 4 and 8 ranks: everything multiply_host_panels (csrc/multiply_exec.cu) asks for before it pipelines the host-pointer
+    multiply as c = 4 column panels holds on every rank -- the layout can be cut, the panel problem (m, n / 4, k) keeps the strategy,
+    local A is shared, local B / C are a quarter each, the panel's A arena fits the plan's. On 2 ranks (pk2: nothing is gathered) the plain
+    path is taken, which streams A and B under the kernel."""
+    from cosma_b200.distributed import MultiplyPlan
+    from panel_cut import host_panel
+    N, c = 32768, 4
+    for P, gathered in ((2, set()), (4, {0}), (8, {0, 1})):
+        full = [MultiplyPlan(None, N, N, N, "", "d", rank=r, nranks=P, allocate=False) for r in range(P)]
+        steps = full[0].strategy
+        sub = [MultiplyPlan(None, N, N // c, N, steps, "d", rank=r, nranks=P, allocate=False) for r in range(P)]
+        assert {o["matrix"] for o in full[0].ops() if o["kind"] == "allgather"} == gathered
+        for r in range(P):
+            assert sum(o["kind"] == "gemm" for o in full[r].ops()) == 1 and sub[r].strategy == steps
+            assert all(host_panel(lib, full[r].handle, c, j)[0] for j in range(c))
+            assert sub[r].initial_elements[0] == full[r].initial_elements[0] and sub[r].arena_elements[0] <= full[r].arena_elements[0]
+            assert sub[r].initial_elements[1] * c == full[r].initial_elements[1] and sub[r].initial_elements[2] * c == full[r].initial_elements[2]
+            pieces = [host_panel(lib, full[r].handle, c, j) for j in range(c)]
+            assert all(sum(p[1] for p in bp) == sub[r].initial_elements[1] and sum(p[1] for p in cp) == sub[r].initial_elements[2] for _, bp, cp in pieces)
+        for pl in full + sub:
+            pl.destroy()
